@@ -1,0 +1,844 @@
+// rt_kernel.cuh — the camera render pass as ONE persistent sm_100a kernel.
+//
+// Replaces, per pixel, Camera::render_parallel (composites/camera.rs:97-112) and everything under
+// World::color_at (composites/world.rs:89-95).  Citations are paths under the reference's
+// `ray-tracer/src/`.
+//
+// Design (B200-first, not a translation of the recursive, trait-object reference):
+//   * every lane is a small state machine that owns one pixel at a time and always has exactly
+//     ONE ray in flight: a radiance ray (nearest hit), a shadow ray (any hit) or a "container"
+//     re-trace (refractive-index bookkeeping).  All three share ONE brute-force intersection loop
+//     over the type-sorted shape table, so the dominant loop runs warp-converged no matter how far
+//     the lanes' recursion trees have drifted apart;
+//   * the reference's recursion (reflected_color / refracted_color, world.rs:114-157) becomes an
+//     explicit post-order stack of <= max_depth frames per lane.  Children are fully evaluated and
+//     only then scaled and added, exactly like the reference (`surface + reflected + refracted`),
+//     so the f64 result is bit-comparable;
+//   * the reference sorts every intersection list (world.rs:34) only to find the hit and to walk the
+//     refraction containers; here the hit is a running (t, world-order) minimum and the container
+//     walk is a second pass that needs no list (see ContainerAcc);
+//   * lanes that finish a pixel refill from a warp-private chunk of pixel slots (8x4 tiles), so a
+//     warp stays full until the frame runs out of pixels;
+//   * arithmetic: this file must be compiled with -fmad=false.  `fma()` appears exactly where the
+//     reference calls `mul_add`; everything else keeps the reference's operation order.
+#pragma once
+
+#include <cfloat>
+#include <cstdint>
+
+#include "rt_scene.h"
+
+namespace rt {
+
+#ifndef RT_STRICT_SIGNED_ZERO
+// 1: keep the reference's `0.0 + ...` fold seeds and `+ m[r][3] * w` terms of Matrix*Point/Vector
+//    (matrix.rs:332-362) literally.  They can only change the SIGN of an exactly-zero component.
+#define RT_STRICT_SIGNED_ZERO 1
+#endif
+
+template <typename T>
+struct Real;
+template <>
+struct Real<double> {
+    static __device__ __forceinline__ double eps() { return 0.00000008; }  // consts.rs:2
+    static __device__ __forceinline__ double offset_eps() { return 0.00000008; }  // computed_hit.rs:33-34
+    static __device__ __forceinline__ double max() { return DBL_MAX; }
+};
+template <>
+struct Real<float> {
+    static __device__ __forceinline__ float eps() { return 0.00000008f; }
+    // 8e-8 is below one f32 ulp at |x| >= 1: the fast mode needs its own offset.
+    static __device__ __forceinline__ float offset_eps() { return 1.0e-3f; }
+    static __device__ __forceinline__ float max() { return FLT_MAX; }
+};
+
+template <typename T>
+struct V3 {
+    T x, y, z;
+};
+template <typename T>
+struct Ray {
+    V3<T> o, d;
+};
+
+#define RT_DEV __device__ __forceinline__
+
+template <typename T> RT_DEV V3<T> mk(T x, T y, T z) { V3<T> r; r.x = x; r.y = y; r.z = z; return r; }
+template <typename T> RT_DEV V3<T> ld3(const T* p) { return mk<T>(p[0], p[1], p[2]); }
+template <typename T> RT_DEV V3<T> operator+(V3<T> a, V3<T> b) { return mk<T>(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <typename T> RT_DEV V3<T> operator-(V3<T> a, V3<T> b) { return mk<T>(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <typename T> RT_DEV V3<T> operator*(V3<T> a, T s) { return mk<T>(a.x * s, a.y * s, a.z * s); }
+template <typename T> RT_DEV V3<T> hadamard(V3<T> a, V3<T> b) { return mk<T>(a.x * b.x, a.y * b.y, a.z * b.z); }
+template <typename T> RT_DEV V3<T> neg(V3<T> a) { return mk<T>(-a.x, -a.y, -a.z); }
+template <typename T> RT_DEV T sq(T v) { return v * v; }  // utils.rs:27-32
+
+// vector.rs:93-95
+template <typename T> RT_DEV T dot(V3<T> a, V3<T> b) { return fma(a.z, b.z, fma(a.x, b.x, a.y * b.y)); }
+// vector.rs:97-103
+template <typename T> RT_DEV V3<T> cross(V3<T> a, V3<T> b) {
+    return mk<T>(fma(a.y, b.z, -a.z * b.y), fma(a.z, b.x, -a.x * b.z), fma(a.x, b.y, -a.y * b.x));
+}
+// vector.rs:84-86
+template <typename T> RT_DEV T magnitude(V3<T> a) { return sqrt(sq(a.x) + sq(a.y) + sq(a.z)); }
+// vector.rs:88-91 (divides)
+template <typename T> RT_DEV V3<T> normalized(V3<T> a) { T m = magnitude(a); return mk<T>(a.x / m, a.y / m, a.z / m); }
+// vector.rs:105-107
+template <typename T> RT_DEV V3<T> reflect(V3<T> v, V3<T> n) { return v - ((n * T(2)) * dot(v, n)); }
+
+// matrix.rs:332-346: Matrix<4> * Point, rows 0..2
+template <typename T> RT_DEV V3<T> mat_point(const T* m, V3<T> p) {
+#if RT_STRICT_SIGNED_ZERO
+    return mk<T>((((T(0) + m[0] * p.x) + m[1] * p.y) + m[2] * p.z) + m[3] * T(1),
+                 (((T(0) + m[4] * p.x) + m[5] * p.y) + m[6] * p.z) + m[7] * T(1),
+                 (((T(0) + m[8] * p.x) + m[9] * p.y) + m[10] * p.z) + m[11] * T(1));
+#else
+    return mk<T>(((m[0] * p.x + m[1] * p.y) + m[2] * p.z) + m[3], ((m[4] * p.x + m[5] * p.y) + m[6] * p.z) + m[7],
+                 ((m[8] * p.x + m[9] * p.y) + m[10] * p.z) + m[11]);
+#endif
+}
+// matrix.rs:348-362: Matrix<4> * Vector
+template <typename T> RT_DEV V3<T> mat_vector(const T* m, V3<T> v) {
+#if RT_STRICT_SIGNED_ZERO
+    return mk<T>((((T(0) + m[0] * v.x) + m[1] * v.y) + m[2] * v.z) + m[3] * T(0),
+                 (((T(0) + m[4] * v.x) + m[5] * v.y) + m[6] * v.z) + m[7] * T(0),
+                 (((T(0) + m[8] * v.x) + m[9] * v.y) + m[10] * v.z) + m[11] * T(0));
+#else
+    return mk<T>((m[0] * v.x + m[1] * v.y) + m[2] * v.z, (m[4] * v.x + m[5] * v.y) + m[6] * v.z,
+                 (m[8] * v.x + m[9] * v.y) + m[10] * v.z);
+#endif
+}
+// shapes/shape.rs:25: transformation_inverse.transpose() * local_normal (row 3 of the inverse is 0,0,0,1)
+template <typename T> RT_DEV V3<T> mat_transposed_vector(const T* m, V3<T> v) {
+#if RT_STRICT_SIGNED_ZERO
+    return mk<T>((((T(0) + m[0] * v.x) + m[4] * v.y) + m[8] * v.z) + T(0),
+                 (((T(0) + m[1] * v.x) + m[5] * v.y) + m[9] * v.z) + T(0),
+                 (((T(0) + m[2] * v.x) + m[6] * v.y) + m[10] * v.z) + T(0));
+#else
+    return mk<T>((m[0] * v.x + m[4] * v.y) + m[8] * v.z, (m[1] * v.x + m[5] * v.y) + m[9] * v.z,
+                 (m[2] * v.x + m[6] * v.y) + m[10] * v.z);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// The scene as the kernel sees it (shared memory when it fits, else global).
+template <typename T>
+struct SceneView {
+    const T* reals;
+    const int* ints;
+    SceneLayout L;
+    RT_DEV const T* shape(uint32_t pos) const { return reals + (size_t)pos * SHAPE_REALS; }
+    RT_DEV int4 shape_meta(uint32_t pos) const { return reinterpret_cast<const int4*>(ints)[pos]; }
+    RT_DEV const T* triangle(uint32_t pos) const { return reals + L.tri_off + (size_t)(pos - L.type_begin[5]) * TRI_REALS; }
+    RT_DEV const T* material(uint32_t m) const { return reals + L.mat_off + (size_t)m * MAT_REALS; }
+    RT_DEV int material_pattern(uint32_t m) const { return ints[L.mat_meta_off + m * MAT_INTS]; }
+    RT_DEV const T* pattern(uint32_t p) const { return reals + L.pat_off + (size_t)p * PAT_REALS; }
+    RT_DEV const int* pattern_meta(uint32_t p) const { return ints + L.pat_meta_off + p * PAT_INTS; }
+    RT_DEV const T* light(uint32_t l) const { return reals + L.light_off + (size_t)l * LIGHT_REALS; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// What one trace accumulates.  Three query kinds share the intersection loop:
+//   RADIANCE  : Intersections::hit (intersections.rs:13-18) = the first minimal distance >= 0 of the
+//               stable-sorted list (world.rs:34), i.e. the minimum of (distance, world order).
+//   SHADOW    : World::is_in_shadow (world.rs:98-112) = any casts_shadow shape with 0 <= t < light
+//               distance — a nearest-hit query seeded with best_t = light distance.
+//   CONTAINER : the refraction-container walk of Intersection::prepare_computations
+//               (intersection.rs:33-62) without materialising the sorted list; see ContainerAcc.
+enum : int { MODE_RADIANCE = 0, MODE_SHADOW = 1, MODE_CONTAINER = 2, MODE_IDLE = 3 };
+
+// The walk toggles each shape class at every intersection that sorts before the hit, i.e. with
+// distance < hit distance (the hit is the FIRST entry with its distance).  A class is in the
+// container list iff it has an odd number of such intersections; its place in the list is the
+// sort position of its last one, (max distance, world order).  n1 = refractive index of the last
+// class in the list; n2 = the same after toggling the hit's own class (intersection.rs:39-58).
+template <typename T>
+struct ContainerAcc {
+    T t_hit;
+    int hit_class;
+    bool hit_class_inside;  // the hit's class is in the list before the hit toggles it
+    int all_pos, excl_pos;  // sorted position of the last class overall / excluding the hit's class; -1 = none
+    T all_t, excl_t;
+    int all_orig, excl_orig;
+};
+
+template <typename T>
+struct TraceAcc {
+    int mode;
+    T best_t;       // RADIANCE: +max seed; SHADOW: light distance seed
+    int best_orig;  // world order of the best hit (tie-break), INT_MAX seed
+    int best_pos;   // sorted position of the best hit, -1 = none
+    ContainerAcc<T> c;
+};
+
+template <typename T>
+RT_DEV void consume(TraceAcc<T>& a, int n, T t0, T t1, T t2, T t3, int pos, int4 meta) {
+    if (a.mode != MODE_CONTAINER) {
+        // intersections.rs:13-18 / intersection.rs:77-79.  NaN fails `t >= 0`.
+        bool eligible = (a.mode == MODE_RADIANCE) || (meta.z & FLAG_CASTS_SHADOW);
+        if (eligible) {
+            const T ts[4] = {t0, t1, t2, t3};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k < n) {
+                    T t = ts[k];
+                    if (t >= T(0) && (t < a.best_t || (t == a.best_t && meta.x < a.best_orig))) {
+                        a.best_t = t;
+                        a.best_orig = meta.x;
+                        a.best_pos = pos;
+                    }
+                }
+            }
+        }
+    } else if (meta.z & FLAG_CONTAINER_REP) {
+        const T ts[4] = {t0, t1, t2, t3};
+        int count = 0;
+        T tmax = -Real<T>::max();
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k < n && ts[k] < a.c.t_hit) {
+                ++count;
+                if (!any || ts[k] > tmax) tmax = ts[k];
+                any = true;
+            }
+        }
+        if (count & 1) {
+            if (meta.w == a.c.hit_class) {
+                a.c.hit_class_inside = true;
+            } else if (a.c.excl_pos < 0 || tmax > a.c.excl_t || (tmax == a.c.excl_t && meta.x > a.c.excl_orig)) {
+                a.c.excl_pos = pos;
+                a.c.excl_t = tmax;
+                a.c.excl_orig = meta.x;
+            }
+            if (a.c.all_pos < 0 || tmax > a.c.all_t || (tmax == a.c.all_t && meta.x > a.c.all_orig)) {
+                a.c.all_pos = pos;
+                a.c.all_t = tmax;
+                a.c.all_orig = meta.x;
+            }
+        }
+    }
+}
+
+// utils.rs:47-57
+template <typename T>
+RT_DEV bool solve_quadratic(T a, T b, T c, T& s1, T& s2) {
+    T discriminant = fma(T(4) * a, -c, sq(b));
+    if (discriminant < T(0)) return false;
+    T double_a = T(2) * a;
+    T root = sqrt(discriminant);
+    s1 = (-b - root) / double_a;
+    s2 = (-b + root) / double_a;
+    return true;
+}
+
+// shapes/cube.rs:22-43
+template <typename T>
+RT_DEV void cube_check_axis(T origin, T direction, T& tmin, T& tmax) {
+    T nmin = T(-1) - origin;
+    T nmax = T(1) - origin;
+    T dmin, dmax;
+    if (fabs(direction) >= Real<T>::eps()) {
+        dmin = nmin / direction;
+        dmax = nmax / direction;
+    } else {
+        dmin = nmin * Real<T>::max();
+        dmax = nmax * Real<T>::max();
+    }
+    if (dmin > dmax) {
+        T t = dmin;
+        dmin = dmax;
+        dmax = t;
+    }
+    tmin = dmin;
+    tmax = dmax;
+}
+
+// cylinder.rs:34-39 / cone.rs:34-39 (radius 1 for the cylinder)
+template <typename T>
+RT_DEV bool check_cap(const Ray<T>& r, T distance, T radius_sq) {
+    T x = fma(r.d.x, distance, r.o.x);
+    T z = fma(r.d.z, distance, r.o.z);
+    return (sq(x) + sq(z)) <= radius_sq;
+}
+
+// local_intersect of shape type TYPE on the object-space ray `r`; distances in push order.
+template <typename T, int TYPE>
+RT_DEV int local_intersect(const Ray<T>& r, const T* g, int flags, const T* tri, T& t0, T& t1, T& t2, T& t3) {
+    int n = 0;
+    T ts[4] = {T(0), T(0), T(0), T(0)};
+    if (TYPE == 0) {  // shapes/sphere.rs:41-53
+        T a = dot(r.d, r.d);
+        T b = T(2) * dot(r.d, r.o);
+        T c = dot(r.o, r.o) - T(1);
+        T s1, s2;
+        if (solve_quadratic(a, b, c, s1, s2)) {
+            ts[0] = s1;
+            ts[1] = s2;
+            n = 2;
+        }
+    } else if (TYPE == 1) {  // shapes/plane.rs:42-48
+        if (!(fabs(r.d.y) < Real<T>::eps())) {
+            ts[0] = -r.o.y / r.d.y;
+            n = 1;
+        }
+    } else if (TYPE == 2) {  // shapes/cube.rs:65-85
+        T xmin, xmax, ymin, ymax, zmin, zmax;
+        cube_check_axis(r.o.x, r.d.x, xmin, xmax);
+        cube_check_axis(r.o.y, r.d.y, ymin, ymax);
+        cube_check_axis(r.o.z, r.d.z, zmin, zmax);
+        T dmin = fmax(fmax(fmax(-Real<T>::max(), xmin), ymin), zmin);
+        T dmax = fmin(fmin(fmin(Real<T>::max(), xmax), ymax), zmax);
+        if (dmin < dmax && dmax > T(0)) {
+            ts[0] = dmin;
+            ts[1] = dmax;
+            n = 2;
+        }
+    } else if (TYPE == 3) {  // shapes/cylinder.rs:81-110 + 41-59
+        T mn = g[SHAPE_MIN], mx = g[SHAPE_MAX];
+        T a = sq(r.d.x) + sq(r.d.z);
+        if (fabs(a) > T(0)) {
+            T b = T(2) * fma(r.o.x, r.d.x, r.o.z * r.d.z);
+            T c = sq(r.o.x) + sq(r.o.z) - T(1);
+            T d1, d2;
+            if (solve_quadratic(a, b, c, d1, d2)) {
+                if (d1 > d2) {
+                    T t = d1;
+                    d1 = d2;
+                    d2 = t;
+                }
+                T y1 = fma(d1, r.d.y, r.o.y);
+                if (mn < y1 && y1 < mx) ts[n++] = d1;
+                T y2 = fma(d2, r.d.y, r.o.y);
+                if (mn < y2 && y2 < mx) ts[n++] = d2;
+            }
+        }
+        if ((flags & FLAG_CLOSED) && !(fabs(r.d.y) < Real<T>::eps())) {
+            T d = (mn - r.o.y) / r.d.y;
+            if (check_cap(r, d, T(1))) ts[n++] = d;
+            d = (mx - r.o.y) / r.d.y;
+            if (check_cap(r, d, T(1))) ts[n++] = d;
+        }
+    } else if (TYPE == 4) {  // shapes/cone.rs:81-112 + 41-59
+        T mn = g[SHAPE_MIN], mx = g[SHAPE_MAX];
+        T a = sq(r.d.x) - sq(r.d.y) + sq(r.d.z);
+        T b = T(2) * fma(r.o.z, r.d.z, fma(r.o.x, r.d.x, -r.o.y * r.d.y));
+        T c = sq(r.o.x) - sq(r.o.y) + sq(r.o.z);
+        T d1, d2;
+        if (fabs(a) < Real<T>::eps() && fabs(b) > Real<T>::eps()) {
+            ts[n++] = -c / (T(2) * b);
+        } else if (solve_quadratic(a, b, c, d1, d2)) {
+            if (d1 > d2) {
+                T t = d1;
+                d1 = d2;
+                d2 = t;
+            }
+            T y1 = fma(r.d.y, d1, r.o.y);
+            if (mn < y1 && y1 < mx) ts[n++] = d1;
+            T y2 = fma(r.d.y, d2, r.o.y);
+            if (mn < y2 && y2 < mx) ts[n++] = d2;
+        }
+        if ((flags & FLAG_CLOSED) && !(fabs(r.d.y) < Real<T>::eps())) {
+            T d = (mn - r.o.y) / r.d.y;
+            if (check_cap(r, d, sq(mn))) ts[n++] = d;
+            d = (mx - r.o.y) / r.d.y;
+            if (check_cap(r, d, sq(mx))) ts[n++] = d;
+        }
+    } else {  // shapes/triangle.rs:39-56
+        V3<T> v1 = ld3(tri), e1 = ld3(tri + 3), e2 = ld3(tri + 6);
+        V3<T> dce2 = cross(r.d, e2);
+        T det = dot(e1, dce2);
+        if (!(fabs(det) < Real<T>::eps())) {
+            V3<T> v1o = r.o - v1;
+            T u = dot(v1o, dce2) / det;
+            if (u >= T(0) && u <= T(1)) {
+                V3<T> oce1 = cross(v1o, e1);
+                T v = dot(r.d, oce1) / det;
+                if (v > T(0) && u + v < T(1)) {
+                    ts[0] = dot(e2, oce1) / det;
+                    n = 1;
+                }
+            }
+        }
+    }
+    t0 = ts[0];
+    t1 = ts[1];
+    t2 = ts[2];
+    t3 = ts[3];
+    return n;
+}
+
+// World::collect_intersections (world.rs:25-35) for one shape type: every shape, no dispatch.
+template <typename T, int TYPE>
+RT_DEV void trace_type(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
+    const uint32_t b = sv.L.type_begin[TYPE], e = sv.L.type_begin[TYPE + 1];
+    for (uint32_t pos = b; pos < e; ++pos) {
+        const T* g = sv.shape(pos);
+        int4 meta = sv.shape_meta(pos);
+        // ray.rs:45-49
+        Ray<T> local;
+        local.o = mat_point(g, ray.o);
+        local.d = mat_vector(g, ray.d);
+        T t0, t1, t2, t3;
+        int n = local_intersect<T, TYPE>(local, g, meta.z, TYPE == 5 ? sv.triangle(pos) : nullptr, t0, t1, t2, t3);
+        consume(acc, n, t0, t1, t2, t3, (int)pos, meta);
+    }
+}
+
+template <typename T>
+RT_DEV void trace(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
+    trace_type<T, 0>(sv, ray, acc);
+    trace_type<T, 1>(sv, ray, acc);
+    trace_type<T, 2>(sv, ray, acc);
+    trace_type<T, 3>(sv, ray, acc);
+    trace_type<T, 4>(sv, ray, acc);
+    trace_type<T, 5>(sv, ray, acc);
+}
+
+RT_DEV int shape_type_of(const SceneLayout& L, uint32_t pos) {
+    int t = 0;
+#pragma unroll
+    for (int k = 1; k < NUM_SHAPE_TYPES; ++k) t += (pos >= L.type_begin[k]) ? 1 : 0;
+    return t;
+}
+
+// utils.rs:16-24
+template <typename T> RT_DEV bool coarse_eq(T a, T b) { return a == b || fabs(a - b) < Real<T>::eps(); }
+
+// local_normal_at of the six shapes (sphere.rs:57-59, plane.rs:52-54, cube.rs:89-101,
+// cylinder.rs:114-126, cone.rs:116-133, triangle.rs:78-80)
+template <typename T>
+RT_DEV V3<T> local_normal_at(const SceneView<T>& sv, uint32_t pos, int type, const T* g, V3<T> p) {
+    switch (type) {
+    case 0: return p;
+    case 1: return mk<T>(T(0), T(1), T(0));
+    case 2: {
+        T ax = fabs(p.x), ay = fabs(p.y), az = fabs(p.z);
+        T mx = fmax(fmax(fmax(-Real<T>::max(), ax), ay), az);
+        if (coarse_eq(mx, ax)) return mk<T>(p.x, T(0), T(0));
+        if (coarse_eq(mx, ay)) return mk<T>(T(0), p.y, T(0));
+        return mk<T>(T(0), T(0), p.z);
+    }
+    case 3: {
+        T dist = sq(p.x) + sq(p.z);
+        if (dist < T(1) && p.y >= (g[SHAPE_MAX] - Real<T>::eps())) return mk<T>(T(0), T(1), T(0));
+        if (dist < T(1) && p.y <= (g[SHAPE_MIN] + Real<T>::eps())) return mk<T>(T(0), T(-1), T(0));
+        return mk<T>(p.x, T(0), p.z);
+    }
+    case 4: {
+        T dist = sq(p.x) + sq(p.z);
+        if (dist < sq(g[SHAPE_MAX]) && p.y >= (g[SHAPE_MAX] - Real<T>::eps())) return mk<T>(T(0), T(1), T(0));
+        if (dist < sq(g[SHAPE_MIN]) && p.y <= (g[SHAPE_MIN] + Real<T>::eps())) return mk<T>(T(0), T(-1), T(0));
+        T y = sqrt(dist);
+        if (p.y > T(0)) y = -y;
+        return mk<T>(p.x, y, p.z);
+    }
+    default: return ld3(sv.triangle(pos) + 9);
+    }
+}
+
+// Rust `f64 as i64` (saturating, NaN -> 0) followed by `% 2 == 0`
+template <typename T>
+RT_DEV bool even_as_i64(T v) {
+    if (v != v) return true;                               // NaN as i64 = 0
+    if (v >= T(9223372036854775808.0)) return false;       // saturates to i64::MAX (odd)
+    if (v <= T(-9223372036854775808.0)) return true;       // saturates to i64::MIN (even)
+    return (((long long)v) % 2) == 0;
+}
+
+// Pattern::color_at (patterns/*.rs) at pattern-space point p
+template <typename T>
+RT_DEV V3<T> pattern_color_at(const SceneView<T>& sv, int pattern, V3<T> p) {
+    for (;;) {
+        const T* pr = sv.pattern(pattern);
+        const int* pm = sv.pattern_meta(pattern);
+        V3<T> a = ld3(pr), b = ld3(pr + 3);
+        switch (pm[0]) {
+        case 0: return even_as_i64(floor(p.x)) ? a : b;  // stripe_pattern.rs:24-31
+        case 1: {                                        // gradient_pattern.rs:24-31
+            V3<T> distance = b - a;
+            T fraction = fabs(p.x - trunc(p.x));
+            if (!even_as_i64(p.x)) fraction = T(1) - fraction;
+            return a + (distance * fraction);
+        }
+        case 2: return even_as_i64(floor(sqrt(sq(p.x) + sq(p.z)))) ? a : b;   // ring_pattern.rs:25-32
+        case 3: return even_as_i64(floor(p.x) + floor(p.y) + floor(p.z)) ? a : b;  // checker_pattern.rs:24-31
+        case 4: pattern = even_as_i64(floor(p.x)) ? pm[1] : pm[2]; break;  // complex_pattern.rs:24-33
+        default: return p;                                                 // TestPattern, pattern.rs:62-66
+        }
+    }
+}
+
+// One frame of the explicit recursion stack = one World::shade_hit in flight (world.rs:38-67).
+template <typename T>
+struct Frame {
+    V3<T> a;         // reflect direction until the reflect child is launched, then the reflected colour
+    V3<T> surface;   // sum over lights (world.rs:43-53)
+    V3<T> refr_o;    // refracted ray origin (world.rs:152) until that child is launched, then the refracted colour
+    V3<T> refr_d;    // refracted ray direction
+    T reflectance;   // Schlick (computed_hit.rs:50-68), only when reflective && transparent
+    T k_reflect, k_transparent;
+    int flags;
+};
+enum : int { FR_REFLECT = 1, FR_REFRACT = 2, FR_SCHLICK = 4, FR_WAIT_REFLECT = 8, FR_WAIT_REFRACT = 16 };
+
+enum : int { ST_FETCH = 0, ST_RADIANCE = 1, ST_CONTAINER = 2, ST_SHADOW = 3, ST_DONE = 4 };
+
+#ifndef RT_BLOCK_THREADS
+#define RT_BLOCK_THREADS 128
+#endif
+#ifndef RT_MIN_BLOCKS_PER_SM
+#define RT_MIN_BLOCKS_PER_SM 3
+#endif
+
+constexpr int TILE_W = 8, TILE_H = 4;   // a warp's 32 pixel slots = one 8x4 tile
+constexpr int CHUNK_SLOTS = 64;         // slots a warp takes from the global counter at a time
+
+template <typename T, int MAX_FRAMES>
+__global__ void __launch_bounds__(RT_BLOCK_THREADS, RT_MIN_BLOCKS_PER_SM)
+render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, SceneLayout layout, CameraParams<T> cam,
+              T* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8, unsigned long long* __restrict__ counters,
+              unsigned int* __restrict__ work_counter) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SceneView<T> sv;
+    sv.L = layout;
+    if (layout.in_shared) {
+        T* s_reals = reinterpret_cast<T*>(smem_raw);
+        int* s_ints = reinterpret_cast<int*>(smem_raw + (((size_t)layout.n_reals * sizeof(T) + 15) & ~size_t(15)));
+        for (uint32_t i = threadIdx.x; i < layout.n_reals; i += blockDim.x) s_reals[i] = g_reals[i];
+        for (uint32_t i = threadIdx.x; i < layout.n_ints; i += blockDim.x) s_ints[i] = g_ints[i];
+        __syncthreads();
+        sv.reals = s_reals;
+        sv.ints = s_ints;
+    } else {
+        sv.reals = g_reals;
+        sv.ints = g_ints;
+    }
+
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t tiles_x = (cam.hsize + TILE_W - 1) / TILE_W;
+    const uint32_t tiles_y = (cam.n_rows + TILE_H - 1) / TILE_H;
+    const uint32_t total_slots = tiles_x * tiles_y * (TILE_W * TILE_H);
+    const int n_lights = (int)layout.n_lights;
+
+    Frame<T> stack[MAX_FRAMES];
+
+    // lane state
+    int state = ST_FETCH;
+    int depth = 0;
+    Ray<T> ray;
+    ray.o = mk<T>(T(0), T(0), T(0));
+    ray.d = mk<T>(T(0), T(0), T(1));
+    size_t out_index = 0;
+    // current node
+    V3<T> over = mk<T>(T(0), T(0), T(0)), under = over, normal = over, eye = over, base = over, surface = over;
+    T t_hit = T(0), shadow_distance = T(0);
+    int hit_pos = -1, hit_material = 0, light = 0;
+    V3<T> node_dir = over;  // direction of the node's radiance ray (for the reflect vector)
+    // warp-private chunk of pixel slots
+    uint32_t chunk_next = 0, chunk_end = 0;
+    bool exhausted = false;
+    // counters
+    unsigned int c_primary = 0, c_shadow = 0, c_reflect = 0, c_refract = 0, c_nodes = 0;
+
+    for (;;) {
+        // ---- phase A: idle lanes take the next pixel slot of the warp's chunk ---------------------
+        {
+            if (exhausted && state == ST_FETCH) state = ST_DONE;
+            unsigned need = __ballot_sync(0xffffffffu, state == ST_FETCH);
+            while (need) {
+                if (chunk_next >= chunk_end) {
+                    uint32_t base_slot = 0;
+                    if (lane == 0) base_slot = atomicAdd(work_counter, (unsigned)CHUNK_SLOTS);
+                    base_slot = __shfl_sync(0xffffffffu, base_slot, 0);
+                    chunk_next = base_slot;
+                    chunk_end = base_slot + CHUNK_SLOTS;
+                    if (base_slot >= total_slots) {  // frame exhausted
+                        if (state == ST_FETCH) state = ST_DONE;
+                        exhausted = true;
+                        break;
+                    }
+                }
+                unsigned rank = __popc(need & ((1u << lane) - 1u));
+                uint32_t avail = chunk_end - chunk_next;
+                bool mine = (state == ST_FETCH) && rank < avail;
+                if (mine) {
+                    uint32_t slot = chunk_next + rank;
+                    state = ST_DONE;  // unless the slot is a real pixel
+                    if (slot < total_slots) {
+                        uint32_t tile = slot / (TILE_W * TILE_H), in = slot % (TILE_W * TILE_H);
+                        uint32_t x = (tile % tiles_x) * TILE_W + in % TILE_W;
+                        uint32_t k = (tile / tiles_x) * TILE_H + in / TILE_W;
+                        state = ST_FETCH;  // padding slot: try again on the next round
+                        if (x < cam.hsize && k < cam.n_rows) {
+                            uint32_t y = ((k / cam.band_rows) * cam.shard_count + cam.shard_index) * cam.band_rows + k % cam.band_rows;
+                            // Camera::ray_for_pixel, camera.rs:52-68
+                            T offset_x = (T(x) + T(0.5)) * cam.pixel_size;
+                            T offset_y = (T(y) + T(0.5)) * cam.pixel_size;
+                            T world_x = cam.half_width - offset_x;
+                            T world_y = cam.half_height - offset_y;
+                            V3<T> pixel = mat_point(cam.inv, mk<T>(world_x, world_y, T(-1)));
+                            V3<T> origin = ld3(cam.origin);
+                            ray.o = origin;
+                            ray.d = normalized(pixel - origin);
+                            out_index = (size_t)k * cam.hsize + x;
+                            depth = 0;
+                            state = ST_RADIANCE;
+                            ++c_primary;
+                        }
+                    } else {
+                        state = ST_DONE;
+                    }
+                }
+                uint32_t taken = min(avail, (uint32_t)__popc(need));
+                chunk_next += taken;
+                need = __ballot_sync(0xffffffffu, state == ST_FETCH);
+            }
+        }
+        if (__all_sync(0xffffffffu, state == ST_DONE)) break;
+
+        // ---- phase B: one trace for every lane that has a ray ----------------------------------------
+        TraceAcc<T> acc;
+        acc.mode = (state == ST_RADIANCE) ? MODE_RADIANCE : (state == ST_SHADOW) ? MODE_SHADOW : (state == ST_CONTAINER) ? MODE_CONTAINER : MODE_IDLE;
+        acc.best_t = (state == ST_SHADOW) ? shadow_distance : Real<T>::max();
+        acc.best_orig = 0x7fffffff;
+        acc.best_pos = -1;
+        acc.c.t_hit = t_hit;
+        acc.c.hit_class = (state == ST_CONTAINER) ? sv.shape_meta((uint32_t)hit_pos).w : -1;
+        acc.c.hit_class_inside = false;
+        acc.c.all_pos = acc.c.excl_pos = -1;
+        acc.c.all_t = acc.c.excl_t = T(0);
+        acc.c.all_orig = acc.c.excl_orig = 0;
+        if (acc.mode != MODE_IDLE) trace(sv, ray, acc);
+
+        // ---- phase C: consume the result ------------------------------------------------------------
+        bool finish_hit = false;     // ComputedHit complete -> start the light loop
+        bool after_lights = false;   // surface colour complete -> children
+        bool returning = false;      // a colour is ready for the parent
+        V3<T> colour = mk<T>(T(0), T(0), T(0));
+        T n1 = T(1), n2 = T(1);  // Material::DEFAULT_REFRACTIVE_INDEX, material.rs:24
+
+        if (state == ST_RADIANCE) {
+            // World::internal_color_at, world.rs:70-86
+            if (acc.best_pos < 0) {
+                returning = true;  // World::DEFAULT_COLOR
+            } else {
+                ++c_nodes;
+                hit_pos = acc.best_pos;
+                t_hit = acc.best_t;
+                const T* g = sv.shape((uint32_t)hit_pos);
+                int4 meta = sv.shape_meta((uint32_t)hit_pos);
+                hit_material = meta.y;
+                // Intersection::prepare_computations, intersection.rs:21-31
+                V3<T> point = ray.o + ray.d * t_hit;
+                V3<T> local_point = mat_point(g, point);  // shape.rs:22-27
+                V3<T> local_normal = local_normal_at(sv, (uint32_t)hit_pos, shape_type_of(sv.L, (uint32_t)hit_pos), g, local_point);
+                normal = normalized(mat_transposed_vector(g, local_normal));
+                eye = neg(ray.d);
+                if (dot(normal, eye) < T(0)) normal = neg(normal);
+                node_dir = ray.d;
+                // computed_hit.rs:33-34
+                over = point + (normal * Real<T>::offset_eps());
+                under = point - (normal * Real<T>::offset_eps());
+                const T* m = sv.material((uint32_t)hit_material);
+                // n1 / n2 feed refracted_color (world.rs:136, needs remaining > 0) and Schlick (world.rs:59,
+                // whose result multiplies black children when remaining == 0): only then walk containers
+                bool need_containers = (m[MAT_TRANSPARENCY] != T(0)) && ((int)cam.max_depth - depth > 0);
+                if (need_containers) state = ST_CONTAINER;  // same ray, container query
+                else finish_hit = true;
+            }
+        } else if (state == ST_CONTAINER) {
+            // intersection.rs:33-62
+            const int hit_mat = hit_material;
+            n1 = (acc.c.all_pos >= 0) ? sv.material((uint32_t)sv.shape_meta((uint32_t)acc.c.all_pos).y)[MAT_REFRACTIVE_INDEX] : T(1);
+            if (acc.c.hit_class_inside)
+                n2 = (acc.c.excl_pos >= 0) ? sv.material((uint32_t)sv.shape_meta((uint32_t)acc.c.excl_pos).y)[MAT_REFRACTIVE_INDEX] : T(1);
+            else
+                n2 = sv.material((uint32_t)hit_mat)[MAT_REFRACTIVE_INDEX];
+            finish_hit = true;
+        } else if (state == ST_SHADOW) {
+            // Material::lighting for light `light`, material.rs:53-114, evaluated at over_point (material.rs:116-130)
+            const T* m = sv.material((uint32_t)hit_material);
+            const T* lt = sv.light((uint32_t)light);
+            V3<T> intensity = ld3(lt + 3);
+            V3<T> effective = hadamard(base, intensity);
+            V3<T> ambient = effective * m[MAT_AMBIENT];
+            V3<T> lit = ambient;
+            bool in_shadow = acc.best_pos >= 0;
+            if (!in_shadow) {
+                V3<T> light_dir = normalized(ld3(lt) - over);
+                T ldn = dot(light_dir, normal);
+                if (!(ldn < T(0))) {
+                    V3<T> diffuse = (effective * m[MAT_DIFFUSE]) * ldn;
+                    V3<T> refl = reflect(neg(light_dir), normal);
+                    T rde = dot(refl, eye);
+                    if (rde <= T(0)) {
+                        lit = ambient + diffuse;
+                    } else {
+                        T factor = pow(rde, m[MAT_SHININESS]);
+                        V3<T> specular = (intensity * m[MAT_SPECULAR]) * factor;
+                        lit = (ambient + diffuse) + specular;
+                    }
+                }
+            }
+            surface = surface + lit;  // fold(Color::BLACK, Color::add), world.rs:53
+            ++light;
+            if (light >= n_lights) after_lights = true;
+        }
+
+        if (finish_hit) {
+            const T* m = sv.material((uint32_t)hit_material);
+            const int remaining = (int)cam.max_depth - depth;
+            Frame<T>& f = stack[depth];
+            f.flags = 0;
+            f.k_reflect = m[MAT_REFLECTIVENESS];
+            f.k_transparent = m[MAT_TRANSPARENCY];
+            f.a = mk<T>(T(0), T(0), T(0));       // reflected colour unless a reflect child runs (world.rs:121)
+            f.refr_o = mk<T>(T(0), T(0), T(0));  // refracted colour unless a refract child runs (world.rs:137,146)
+            if (remaining > 0 && m[MAT_REFLECTIVENESS] != T(0)) {  // world.rs:120
+                f.a = reflect(node_dir, normal);  // intersection.rs:31; replaced by the colour on return
+                f.flags |= FR_REFLECT;
+            }
+            T cos_i = dot(eye, normal);
+            if (remaining > 0 && m[MAT_TRANSPARENCY] != T(0)) {  // world.rs:136-154
+                T n_ratio = n1 / n2;
+                T sin2_t = sq(n_ratio) * (T(1) - sq(cos_i));
+                if (!(sin2_t > T(1))) {
+                    T cos_t = sqrt(T(1) - sin2_t);
+                    f.refr_o = under;
+                    f.refr_d = (normal * fma(n_ratio, cos_i, -cos_t)) - (eye * n_ratio);
+                    f.flags |= FR_REFRACT;
+                }
+            }
+            if (m[MAT_REFLECTIVENESS] > T(0) && m[MAT_TRANSPARENCY] > T(0)) {  // world.rs:59
+                f.flags |= FR_SCHLICK;
+                // ComputedHit::schlicks_approximation, computed_hit.rs:50-68
+                T reflectance;
+                T c = cos_i;
+                bool total = false;
+                if (n1 > n2) {
+                    T ratio = n1 / n2;
+                    T sin2_t = sq(ratio) * (T(1) - sq(c));
+                    if (sin2_t > T(1)) total = true;
+                    else c = sqrt(T(1) - sin2_t);
+                }
+                if (total) {
+                    reflectance = T(1);
+                } else {
+                    T r0 = sq((n1 - n2) / (n1 + n2));
+                    T x = T(1) - c;
+                    T x5 = x * ((x * x) * (x * x));  // powi(5)
+                    reflectance = fma(T(1) - r0, x5, r0);
+                }
+                f.reflectance = reflectance;
+            }
+            // Material::resolve_color, material.rs:75-80 (same for every light of this node)
+            int pat = sv.material_pattern((uint32_t)hit_material);
+            if (pat >= 0) {
+                V3<T> object_point = mat_point(sv.shape((uint32_t)hit_pos), over);  // pattern.rs:10-14
+                V3<T> pattern_point = mat_point(sv.pattern((uint32_t)pat) + 6, object_point);
+                base = pattern_color_at(sv, pat, pattern_point);
+            } else {
+                base = ld3(m);
+            }
+            surface = mk<T>(T(0), T(0), T(0));
+            light = 0;
+            if (n_lights == 0) after_lights = true;
+            else state = ST_SHADOW;
+        }
+
+        if (state == ST_SHADOW && !after_lights) {
+            // World::is_in_shadow, world.rs:98-112: next shadow ray
+            V3<T> to_light = ld3(sv.light((uint32_t)light)) - over;
+            shadow_distance = magnitude(to_light);
+            ray.o = over;
+            ray.d = normalized(to_light);
+            ++c_shadow;
+        }
+
+        if (after_lights) stack[depth].surface = surface;
+
+        // ---- children and returns: World::shade_hit's tail (world.rs:55-66) as a post-order walk ----
+        bool advance = after_lights;
+        while (advance || returning) {
+            if (returning) {
+                if (depth == 0) {  // Camera::render_parallel writes the pixel, camera.rs:108
+                    if (out_rgb) {
+                        out_rgb[out_index * 3 + 0] = colour.x;
+                        out_rgb[out_index * 3 + 1] = colour.y;
+                        out_rgb[out_index * 3 + 2] = colour.z;
+                    }
+                    if (out_rgb8) {  // Canvas::to_png_file, canvas.rs:117-123
+                        const T ch[3] = {colour.x, colour.y, colour.z};
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            T v = ch[k];
+                            v = (v < T(0)) ? T(0) : v;
+                            v = (v > T(1)) ? T(1) : v;
+                            v = round(v * T(255));
+                            out_rgb8[out_index * 3 + k] = (v != v) ? (uint8_t)0 : (uint8_t)v;
+                        }
+                    }
+                    state = ST_FETCH;
+                    break;
+                }
+                --depth;
+                Frame<T>& p = stack[depth];
+                if (p.flags & FR_WAIT_REFLECT) {
+                    p.flags &= ~FR_WAIT_REFLECT;
+                    p.a = colour * p.k_reflect;  // world.rs:127
+                } else {
+                    p.flags &= ~FR_WAIT_REFRACT;
+                    p.refr_o = colour * p.k_transparent;  // world.rs:156
+                }
+                returning = false;
+            }
+            advance = false;
+            Frame<T>& f = stack[depth];
+            if (f.flags & FR_REFLECT) {
+                // World::reflected_color, world.rs:114-128.  Only reachable straight after this node's
+                // light loop, so `over` still is this node's over_point.
+                ray.o = over;
+                ray.d = f.a;
+                f.flags = (f.flags & ~FR_REFLECT) | FR_WAIT_REFLECT;
+                ++depth;
+                state = ST_RADIANCE;
+                ++c_reflect;
+                break;
+            }
+            if (f.flags & FR_REFRACT) {
+                // World::refracted_color, world.rs:130-157
+                ray.o = f.refr_o;
+                ray.d = f.refr_d;
+                f.flags = (f.flags & ~FR_REFRACT) | FR_WAIT_REFRACT;
+                ++depth;
+                state = ST_RADIANCE;
+                ++c_refract;
+                break;
+            }
+            // world.rs:59-66
+            if (f.flags & FR_SCHLICK)
+                colour = (f.surface + (f.a * f.reflectance)) + (f.refr_o * (T(1) - f.reflectance));
+            else
+                colour = (f.surface + f.a) + f.refr_o;
+            returning = true;
+        }
+    }
+
+    // ---- work counters (rays = World::collect_intersections calls) ---------------------------------
+    if (counters) {
+        unsigned int vals[5] = {c_primary, c_shadow, c_reflect, c_refract, c_nodes};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            unsigned int v = vals[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && v) atomicAdd(&counters[k], (unsigned long long)v);
+        }
+        unsigned int px = c_primary;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) px += __shfl_xor_sync(0xffffffffu, px, o);
+        if (lane == 0 && px) atomicAdd(&counters[COUNTER_PIXELS], (unsigned long long)px);
+    }
+}
+
+}  // namespace rt

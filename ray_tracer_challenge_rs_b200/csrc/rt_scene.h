@@ -1,0 +1,91 @@
+// rt_scene.h — device-side scene layout shared by the host packer (rtgpu.cu) and the kernels.
+//
+// The reference keeps `Vec<Box<dyn Shape>>` (composites/world.rs:9-12).  On the device the world is
+// ONE contiguous blob of `T` (double in parity mode, float in fast mode) plus one blob of int32
+// metadata, with the shapes grouped by type so that the intersection loops contain no dispatch:
+//
+//   real blob : [ shape geometry S x 16 ][ triangle data NT x 12 ][ materials M x 12 ]
+//               [ patterns Q x 18 ][ lights L x 6 ]
+//   int  blob : [ shape meta S x 4 ][ material meta M x 2 ][ pattern meta Q x 4 ]
+//
+// Both blobs are staged into shared memory by every CTA when they fit (always, for the shipped
+// scenes: <= 3 KB), otherwise they are read through L1/L2 from global memory.
+#pragma once
+#include <stdint.h>
+
+namespace rt {
+
+// ---- shape geometry record: 16 reals (128 B in f64, 16-byte aligned rows) ---------------------
+//  [0..11]  transformation_inverse rows 0..2 (row-major 3x4)         shapes/shape.rs:31
+//  [12]     min   (cylinder / cone)                                   cylinder.rs:12, cone.rs:12
+//  [13]     max
+//  [14..15] unused (keeps records 16-byte aligned for 128-bit shared loads)
+constexpr int SHAPE_REALS = 16;
+constexpr int SHAPE_MIN = 12;
+constexpr int SHAPE_MAX = 13;
+
+// ---- shape meta record: 4 int32 ---------------------------------------------------------------
+//  [0] orig index in world.shapes (tie-breaks, intersections.rs:13-18 + world.rs:34)
+//  [1] material index
+//  [2] flags
+//  [3] eq_class (lowest orig index of a value-equal shape; intersection.rs:38,47)
+constexpr int SHAPE_INTS = 4;
+constexpr int FLAG_CLOSED = 1;        // cylinder.rs:14 / cone.rs:14
+constexpr int FLAG_CASTS_SHADOW = 2;  // material.casts_shadow of the shape's material (world.rs:108)
+// The refraction-container walk treats value-equal shapes as one (intersection.rs:47).  A class of
+// k identical shapes toggles k times per distinct distance: for even k it never stays in the
+// container list, for odd k it behaves like ONE shape whose last push comes from its highest-index
+// member.  The packer therefore marks exactly that member of every odd-sized class.
+constexpr int FLAG_CONTAINER_REP = 4;
+
+// ---- triangle record: 12 reals (shapes/triangle.rs:9-18) ----------------------------------------
+//  vertex_1[3], edge_1[3], edge_2[3], normal[3]; indexed by (sorted position - first triangle)
+constexpr int TRI_REALS = 12;
+
+// ---- material record: 12 reals (composites/material.rs:9-20) -------------------------------------
+//  color[3], ambient, diffuse, specular, shininess, reflectiveness, transparency, refractive_index, pad[2]
+constexpr int MAT_REALS = 12;
+constexpr int MAT_AMBIENT = 3, MAT_DIFFUSE = 4, MAT_SPECULAR = 5, MAT_SHININESS = 6, MAT_REFLECTIVENESS = 7,
+              MAT_TRANSPARENCY = 8, MAT_REFRACTIVE_INDEX = 9;
+//  material meta: [0] pattern index (-1 none), [1] casts_shadow
+constexpr int MAT_INTS = 2;
+
+// ---- pattern record: 18 reals: color_a[3], color_b[3], transformation_inverse rows 0..2 [12] ----
+constexpr int PAT_REALS = 18;
+//  pattern meta: [0] type (rtgpu_pattern_type), [1] child_a, [2] child_b, [3] pad
+constexpr int PAT_INTS = 4;
+
+// ---- light record: 6 reals: position[3], intensity[3] (primitives/light.rs:6-9) -----------------
+constexpr int LIGHT_REALS = 6;
+
+constexpr int NUM_SHAPE_TYPES = 6;  // order = rtgpu_shape_type: sphere, plane, cube, cylinder, cone, triangle
+
+// What a kernel needs to find its way around the two blobs.  Passed by value as a kernel parameter.
+struct SceneLayout {
+    uint32_t n_shapes;
+    uint32_t type_begin[NUM_SHAPE_TYPES + 1];  // sorted positions [type_begin[t], type_begin[t+1]) hold type t
+    uint32_t n_materials, n_patterns, n_lights;
+    uint32_t tri_off, mat_off, pat_off, light_off;  // offsets into the real blob, in reals
+    uint32_t mat_meta_off, pat_meta_off;            // offsets into the int blob, in int32
+    uint32_t n_reals, n_ints;                       // blob sizes
+    uint32_t in_shared;                             // 1: CTAs stage both blobs in shared memory
+};
+
+// Camera (composites/camera.rs:10-19) + the row selection of one launch (include/rtgpu.h rtgpu_rows).
+template <typename T>
+struct CameraParams {
+    T half_width, half_height, pixel_size;
+    T inv[12];
+    T origin[3];
+    uint32_t hsize, vsize;
+    // rows: compact row k of this launch is image row ((k / band_rows) * shard_count + shard_index) * band_rows + k % band_rows
+    uint32_t n_rows;  // rows rendered by this launch
+    uint32_t band_rows, shard_index, shard_count;
+    uint32_t max_depth;  // World::MAX_REFLECTION_ITERATIONS (world.rs:15)
+};
+
+// Work counters, in the order of the first six fields of rtgpu_stats.
+constexpr int COUNTER_PRIMARY = 0, COUNTER_SHADOW = 1, COUNTER_REFLECT = 2, COUNTER_REFRACT = 3, COUNTER_HIT_NODES = 4,
+              COUNTER_PIXELS = 5, NUM_COUNTERS = 6;
+
+}  // namespace rt

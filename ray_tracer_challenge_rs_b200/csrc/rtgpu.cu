@@ -1,0 +1,656 @@
+// rtgpu.cu — implementation of the C ABI in include/rtgpu.h (host side: scene packer, launcher,
+// row-band sharding across devices, measurement helpers).  The kernels live in rt_kernel.cuh.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo -O3 -shared (see build.py).
+// -fmad=false is REQUIRED: the reference never contracts a*b+c (rt_kernel.cuh, header comment).
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rtgpu.h"
+#include "rt_kernel.cuh"
+#include "rt_scene.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int status, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return status;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(_e == cudaErrorMemoryAllocation ? RTGPU_ERR_OUT_OF_MEMORY : RTGPU_ERR_CUDA, \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Scene packer: rtgpu_scene (world order, SoA) -> the two device blobs of rt_scene.h (type-sorted).
+
+struct PackedScene {
+    std::vector<double> reals;
+    std::vector<int> ints;
+    rt::SceneLayout layout;
+};
+
+int validate_scene(const rtgpu_scene* s) {
+    if (!s) return fail(RTGPU_ERR_INVALID_ARGUMENT, "scene is NULL");
+    if (s->abi_version != RTGPU_ABI_VERSION)
+        return fail(RTGPU_ERR_INVALID_ARGUMENT, "scene.abi_version %u != %u", s->abi_version, RTGPU_ABI_VERSION);
+    const uint32_t S = s->n_shapes, M = s->n_materials, Q = s->n_patterns, L = s->n_lights, NT = s->n_triangles;
+    if (S && (!s->shape_type || !s->shape_inv || !s->shape_min || !s->shape_max || !s->shape_closed ||
+              !s->shape_material || !s->shape_eq_class))
+        return fail(RTGPU_ERR_INVALID_ARGUMENT, "a shape array is NULL");
+    if (M && (!s->mat_color || !s->mat_params || !s->mat_casts_shadow || !s->mat_pattern))
+        return fail(RTGPU_ERR_INVALID_ARGUMENT, "a material array is NULL");
+    if (Q && (!s->pat_type || !s->pat_color_a || !s->pat_color_b || !s->pat_inv || !s->pat_child_a || !s->pat_child_b))
+        return fail(RTGPU_ERR_INVALID_ARGUMENT, "a pattern array is NULL");
+    if (L && (!s->light_position || !s->light_intensity)) return fail(RTGPU_ERR_INVALID_ARGUMENT, "a light array is NULL");
+    if (NT && (!s->tri_vertex_1 || !s->tri_edge_1 || !s->tri_edge_2 || !s->tri_normal || !s->shape_triangle))
+        return fail(RTGPU_ERR_INVALID_ARGUMENT, "a triangle array is NULL");
+    for (uint32_t i = 0; i < S; ++i) {
+        if (s->shape_type[i] >= RTGPU_SHAPE_TYPE_COUNT) return fail(RTGPU_ERR_INVALID_ARGUMENT, "shape %u: type %u", i, s->shape_type[i]);
+        if (s->shape_material[i] >= M) return fail(RTGPU_ERR_INVALID_ARGUMENT, "shape %u: material %u out of range", i, s->shape_material[i]);
+        if (s->shape_eq_class[i] > i) return fail(RTGPU_ERR_INVALID_ARGUMENT, "shape %u: eq_class %u is not the lowest equal index", i, s->shape_eq_class[i]);
+        if (s->shape_type[i] == RTGPU_TRIANGLE && (!s->shape_triangle || s->shape_triangle[i] < 0 || (uint32_t)s->shape_triangle[i] >= NT))
+            return fail(RTGPU_ERR_INVALID_ARGUMENT, "shape %u: triangle index out of range", i);
+    }
+    for (uint32_t m = 0; m < M; ++m)
+        if (s->mat_pattern[m] >= (int32_t)Q) return fail(RTGPU_ERR_INVALID_ARGUMENT, "material %u: pattern %d out of range", m, s->mat_pattern[m]);
+    for (uint32_t q = 0; q < Q; ++q) {
+        if (s->pat_type[q] >= RTGPU_PATTERN_TYPE_COUNT) return fail(RTGPU_ERR_INVALID_ARGUMENT, "pattern %u: type %u", q, s->pat_type[q]);
+        if (s->pat_type[q] == RTGPU_PATTERN_COMPLEX) {
+            // children are emitted before their parent by every flattener: guarantees termination on device
+            if (s->pat_child_a[q] < 0 || s->pat_child_b[q] < 0 || (uint32_t)s->pat_child_a[q] >= q || (uint32_t)s->pat_child_b[q] >= q)
+                return fail(RTGPU_ERR_INVALID_ARGUMENT, "pattern %u: complex children must precede their parent", q);
+        }
+    }
+    return RTGPU_OK;
+}
+
+int pack_scene(const rtgpu_scene* s, PackedScene* out) {
+    int st = validate_scene(s);
+    if (st != RTGPU_OK) return st;
+    const uint32_t S = s->n_shapes, M = s->n_materials, Q = s->n_patterns, L = s->n_lights;
+    rt::SceneLayout& lay = out->layout;
+    memset(&lay, 0, sizeof(lay));
+    lay.n_shapes = S;
+    lay.n_materials = M;
+    lay.n_patterns = Q;
+    lay.n_lights = L;
+
+    // stable grouping by type: world order is kept inside a type (and carried as `orig` for tie-breaks)
+    std::vector<uint32_t> order;
+    order.reserve(S);
+    uint32_t n_tri = 0;
+    for (int t = 0; t < rt::NUM_SHAPE_TYPES; ++t) {
+        lay.type_begin[t] = (uint32_t)order.size();
+        for (uint32_t i = 0; i < S; ++i)
+            if (s->shape_type[i] == t) order.push_back(i);
+    }
+    lay.type_begin[rt::NUM_SHAPE_TYPES] = S;
+    n_tri = lay.type_begin[6] - lay.type_begin[5];
+
+    // value-equal classes: size parity and highest member (rt_scene.h FLAG_CONTAINER_REP)
+    std::vector<uint32_t> class_size(S, 0), class_last(S, 0);
+    for (uint32_t i = 0; i < S; ++i) {
+        class_size[s->shape_eq_class[i]]++;
+        class_last[s->shape_eq_class[i]] = i;
+    }
+
+    lay.tri_off = S * rt::SHAPE_REALS;
+    lay.mat_off = lay.tri_off + n_tri * rt::TRI_REALS;
+    lay.pat_off = lay.mat_off + M * rt::MAT_REALS;
+    lay.light_off = lay.pat_off + Q * rt::PAT_REALS;
+    lay.n_reals = lay.light_off + L * rt::LIGHT_REALS;
+    lay.n_reals = (lay.n_reals + 1u) & ~1u;
+    lay.mat_meta_off = S * rt::SHAPE_INTS;
+    lay.pat_meta_off = lay.mat_meta_off + M * rt::MAT_INTS;
+    lay.n_ints = lay.pat_meta_off + Q * rt::PAT_INTS;
+    lay.n_ints = (lay.n_ints + 3u) & ~3u;
+
+    out->reals.assign(lay.n_reals, 0.0);
+    out->ints.assign(lay.n_ints, 0);
+    double* R = out->reals.data();
+    int* I = out->ints.data();
+
+    for (uint32_t pos = 0; pos < S; ++pos) {
+        const uint32_t i = order[pos];
+        double* g = R + (size_t)pos * rt::SHAPE_REALS;
+        memcpy(g, s->shape_inv + (size_t)i * 12, 12 * sizeof(double));
+        g[rt::SHAPE_MIN] = s->shape_min[i];
+        g[rt::SHAPE_MAX] = s->shape_max[i];
+        const uint32_t mat = s->shape_material[i];
+        const uint32_t cls = s->shape_eq_class[i];
+        int flags = 0;
+        if (s->shape_closed[i]) flags |= rt::FLAG_CLOSED;
+        if (s->mat_casts_shadow[mat]) flags |= rt::FLAG_CASTS_SHADOW;
+        if ((class_size[cls] & 1u) && class_last[cls] == i) flags |= rt::FLAG_CONTAINER_REP;
+        int* m = I + (size_t)pos * rt::SHAPE_INTS;
+        m[0] = (int)i;
+        m[1] = (int)mat;
+        m[2] = flags;
+        m[3] = (int)cls;
+        if (s->shape_type[i] == RTGPU_TRIANGLE) {
+            const size_t t = (size_t)s->shape_triangle[i] * 3;
+            double* td = R + lay.tri_off + (size_t)(pos - lay.type_begin[5]) * rt::TRI_REALS;
+            memcpy(td + 0, s->tri_vertex_1 + t, 3 * sizeof(double));
+            memcpy(td + 3, s->tri_edge_1 + t, 3 * sizeof(double));
+            memcpy(td + 6, s->tri_edge_2 + t, 3 * sizeof(double));
+            memcpy(td + 9, s->tri_normal + t, 3 * sizeof(double));
+        }
+    }
+    for (uint32_t m = 0; m < M; ++m) {
+        double* d = R + lay.mat_off + (size_t)m * rt::MAT_REALS;
+        memcpy(d, s->mat_color + (size_t)m * 3, 3 * sizeof(double));
+        memcpy(d + 3, s->mat_params + (size_t)m * RTGPU_MAT_PARAM_COUNT, RTGPU_MAT_PARAM_COUNT * sizeof(double));
+        I[lay.mat_meta_off + m * rt::MAT_INTS + 0] = s->mat_pattern[m];
+        I[lay.mat_meta_off + m * rt::MAT_INTS + 1] = s->mat_casts_shadow[m] ? 1 : 0;
+    }
+    for (uint32_t q = 0; q < Q; ++q) {
+        double* d = R + lay.pat_off + (size_t)q * rt::PAT_REALS;
+        memcpy(d, s->pat_color_a + (size_t)q * 3, 3 * sizeof(double));
+        memcpy(d + 3, s->pat_color_b + (size_t)q * 3, 3 * sizeof(double));
+        memcpy(d + 6, s->pat_inv + (size_t)q * 12, 12 * sizeof(double));
+        int* pm = I + lay.pat_meta_off + q * rt::PAT_INTS;
+        pm[0] = s->pat_type[q];
+        pm[1] = s->pat_child_a[q];
+        pm[2] = s->pat_child_b[q];
+    }
+    for (uint32_t l = 0; l < L; ++l) {
+        double* d = R + lay.light_off + (size_t)l * rt::LIGHT_REALS;
+        memcpy(d, s->light_position + (size_t)l * 3, 3 * sizeof(double));
+        memcpy(d + 3, s->light_intensity + (size_t)l * 3, 3 * sizeof(double));
+    }
+    return RTGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rows of a launch
+
+struct RowSel {
+    uint32_t band_rows, shard_index, shard_count;
+};
+
+int normalise_rows(const rtgpu_rows* rows, uint32_t vsize, RowSel* out) {
+    RowSel r;
+    r.band_rows = (rows && rows->band_rows) ? rows->band_rows : (vsize ? vsize : 1u);
+    r.shard_count = (rows && rows->shard_count) ? rows->shard_count : 1u;
+    r.shard_index = rows ? rows->shard_index : 0u;
+    if (r.shard_index >= r.shard_count) return fail(RTGPU_ERR_INVALID_ARGUMENT, "rows.shard_index %u >= shard_count %u", r.shard_index, r.shard_count);
+    *out = r;
+    return RTGPU_OK;
+}
+
+uint32_t count_rows(const RowSel& r, uint32_t vsize) {
+    uint32_t n = 0;
+    const uint32_t period = r.band_rows * r.shard_count;
+    // full periods, then the tail
+    const uint32_t full = vsize / period;
+    n = full * r.band_rows;
+    const uint32_t rem = vsize - full * period;
+    const uint32_t lo = r.shard_index * r.band_rows;
+    if (rem > lo) n += std::min(r.band_rows, rem - lo);
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Context: one scene resident on one device
+
+}  // namespace
+
+struct rtgpu_context {
+    int device = 0;
+    rt::SceneLayout layout{};
+    double* d_reals64 = nullptr;
+    float* d_reals32 = nullptr;
+    int* d_ints = nullptr;
+    unsigned int* d_work = nullptr;            // pixel-slot counter of the persistent kernel
+    unsigned long long* d_counters = nullptr;  // rt::NUM_COUNTERS
+    // host-buffer path
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void* d_out = nullptr;
+    size_t d_out_bytes = 0;
+    uint8_t* d_out8 = nullptr;
+    size_t d_out8_bytes = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+};
+
+namespace {
+
+template <typename T, int MAX_FRAMES>
+int launch_kernel(rtgpu_context* ctx, const T* d_reals, const rt::CameraParams<T>& cam, T* d_out, uint8_t* d_out8,
+                  unsigned long long* d_counters, cudaStream_t stream) {
+    auto kernel = rt::render_kernel<T, MAX_FRAMES>;
+    rt::SceneLayout lay = ctx->layout;
+    size_t smem = (((size_t)lay.n_reals * sizeof(T) + 15) & ~size_t(15)) + (size_t)lay.n_ints * sizeof(int);
+    // keep at least ~3 CTAs of 128 threads per SM resident: stage in shared memory only when small enough
+    const size_t smem_cap = std::min<size_t>(ctx->smem_optin, 64 * 1024);
+    lay.in_shared = smem <= smem_cap ? 1u : 0u;
+    if (!lay.in_shared) smem = 0;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks_per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, RT_BLOCK_THREADS, smem));
+    if (blocks_per_sm < 1) return fail(RTGPU_ERR_CUDA, "render kernel does not fit on an SM (smem %zu B)", smem);
+    // persistent grid: every SM full, no more; never more CTAs than there are 64-slot chunks of work
+    const uint64_t slots = (uint64_t)((cam.hsize + rt::TILE_W - 1) / rt::TILE_W) * ((cam.n_rows + rt::TILE_H - 1) / rt::TILE_H) * 32ull;
+    const uint64_t warps_needed = (slots + rt::CHUNK_SLOTS - 1) / rt::CHUNK_SLOTS;
+    const uint64_t blocks_needed = (warps_needed + (RT_BLOCK_THREADS / 32) - 1) / (RT_BLOCK_THREADS / 32);
+    uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)blocks_per_sm;
+    if (grid > blocks_needed) grid = blocks_needed;
+    if (grid < 1) grid = 1;
+    CUDA_TRY(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), stream));
+    kernel<<<(unsigned)grid, RT_BLOCK_THREADS, smem, stream>>>(d_reals, ctx->d_ints, lay, cam, d_out, d_out8, d_counters, ctx->d_work);
+    CUDA_TRY(cudaGetLastError());
+    return RTGPU_OK;
+}
+
+template <typename T>
+void fill_camera(const rtgpu_camera* c, const RowSel& rows, uint32_t n_rows, uint32_t max_depth, rt::CameraParams<T>* out) {
+    out->half_width = (T)c->half_width;
+    out->half_height = (T)c->half_height;
+    out->pixel_size = (T)c->pixel_size;
+    for (int i = 0; i < 12; ++i) out->inv[i] = (T)c->inv[i];
+    for (int i = 0; i < 3; ++i) out->origin[i] = (T)c->origin[i];
+    out->hsize = c->hsize;
+    out->vsize = c->vsize;
+    out->n_rows = n_rows;
+    out->band_rows = rows.band_rows;
+    out->shard_index = rows.shard_index;
+    out->shard_count = rows.shard_count;
+    out->max_depth = max_depth;
+}
+
+int ensure_f32_blob(rtgpu_context* ctx, cudaStream_t stream) {
+    if (ctx->d_reals32 || ctx->layout.n_reals == 0) return RTGPU_OK;
+    std::vector<double> h(ctx->layout.n_reals);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), ctx->d_reals64, h.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    std::vector<float> f(h.size());
+    for (size_t i = 0; i < h.size(); ++i) f[i] = (float)h[i];
+    CUDA_TRY(cudaMalloc(&ctx->d_reals32, f.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(ctx->d_reals32, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return RTGPU_OK;
+}
+
+int check_opts(const rtgpu_opts* opts, uint32_t* precision, uint32_t* max_depth) {
+    *precision = opts ? opts->precision : (uint32_t)RTGPU_PRECISION_F64;
+    *max_depth = opts ? opts->max_depth : 6u;
+    if (*precision != RTGPU_PRECISION_F64 && *precision != RTGPU_PRECISION_F32)
+        return fail(RTGPU_ERR_INVALID_ARGUMENT, "opts.precision %u", *precision);
+    if (*max_depth > 15u) return fail(RTGPU_ERR_INVALID_ARGUMENT, "opts.max_depth %u > 15", *max_depth);
+    return RTGPU_OK;
+}
+
+int render_device_impl(rtgpu_context* ctx, const rtgpu_camera* camera, const rtgpu_opts* opts, const rtgpu_rows* rows,
+                       void* d_out_rgb, uint8_t* d_out_rgb8, uint64_t* d_counters, cudaStream_t stream, uint32_t* out_n_rows) {
+    if (!ctx || !camera) return fail(RTGPU_ERR_INVALID_ARGUMENT, "context or camera is NULL");
+    if (!d_out_rgb && !d_out_rgb8) return fail(RTGPU_ERR_INVALID_ARGUMENT, "both output pointers are NULL");
+    uint32_t precision, max_depth;
+    int st = check_opts(opts, &precision, &max_depth);
+    if (st != RTGPU_OK) return st;
+    RowSel sel;
+    st = normalise_rows(rows, camera->vsize, &sel);
+    if (st != RTGPU_OK) return st;
+    const uint32_t n_rows = count_rows(sel, camera->vsize);
+    if (out_n_rows) *out_n_rows = n_rows;
+    if (n_rows == 0 || camera->hsize == 0) return RTGPU_OK;  // nothing to render
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    unsigned long long* counters = reinterpret_cast<unsigned long long*>(d_counters);
+    if (precision == RTGPU_PRECISION_F64) {
+        rt::CameraParams<double> cam;
+        fill_camera(camera, sel, n_rows, max_depth, &cam);
+        if (max_depth <= 7) return launch_kernel<double, 8>(ctx, ctx->d_reals64, cam, (double*)d_out_rgb, d_out_rgb8, counters, stream);
+        return launch_kernel<double, 16>(ctx, ctx->d_reals64, cam, (double*)d_out_rgb, d_out_rgb8, counters, stream);
+    }
+    st = ensure_f32_blob(ctx, stream);
+    if (st != RTGPU_OK) return st;
+    rt::CameraParams<float> cam;
+    fill_camera(camera, sel, n_rows, max_depth, &cam);
+    if (max_depth <= 7) return launch_kernel<float, 8>(ctx, ctx->d_reals32, cam, (float*)d_out_rgb, d_out_rgb8, counters, stream);
+    return launch_kernel<float, 16>(ctx, ctx->d_reals32, cam, (float*)d_out_rgb, d_out_rgb8, counters, stream);
+}
+
+int upload_scene(rtgpu_context* ctx, const PackedScene& packed) {
+    const rt::SceneLayout& lay = packed.layout;
+    if (ctx->d_reals64) cudaFree(ctx->d_reals64);
+    if (ctx->d_reals32) cudaFree(ctx->d_reals32);
+    if (ctx->d_ints) cudaFree(ctx->d_ints);
+    ctx->d_reals64 = nullptr;
+    ctx->d_reals32 = nullptr;
+    ctx->d_ints = nullptr;
+    ctx->layout = lay;
+    CUDA_TRY(cudaMalloc(&ctx->d_reals64, std::max<size_t>(16, (size_t)lay.n_reals * sizeof(double))));
+    CUDA_TRY(cudaMalloc(&ctx->d_ints, std::max<size_t>(16, (size_t)lay.n_ints * sizeof(int))));
+    if (lay.n_reals) CUDA_TRY(cudaMemcpyAsync(ctx->d_reals64, packed.reals.data(), (size_t)lay.n_reals * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (lay.n_ints) CUDA_TRY(cudaMemcpyAsync(ctx->d_ints, packed.ints.data(), (size_t)lay.n_ints * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return RTGPU_OK;
+}
+
+int context_init(rtgpu_context* ctx, int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(RTGPU_ERR_NO_DEVICE, "no CUDA device available (gpu mode has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return fail(RTGPU_ERR_INVALID_ARGUMENT, "device %d out of range (0..%d)", device, n - 1);
+    ctx->device = device;
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&ctx->ev0));
+    CUDA_TRY(cudaEventCreate(&ctx->ev1));
+    CUDA_TRY(cudaMalloc(&ctx->d_work, sizeof(unsigned int)));
+    CUDA_TRY(cudaMalloc(&ctx->d_counters, rt::NUM_COUNTERS * sizeof(unsigned long long)));
+    return RTGPU_OK;
+}
+
+void context_release(rtgpu_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->d_reals64) cudaFree(ctx->d_reals64);
+    if (ctx->d_reals32) cudaFree(ctx->d_reals32);
+    if (ctx->d_ints) cudaFree(ctx->d_ints);
+    if (ctx->d_work) cudaFree(ctx->d_work);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_out) cudaFree(ctx->d_out);
+    if (ctx->d_out8) cudaFree(ctx->d_out8);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int ensure_out_buffers(rtgpu_context* ctx, size_t rgb_bytes, size_t rgb8_bytes) {
+    if (rgb_bytes > ctx->d_out_bytes) {
+        if (ctx->d_out) cudaFree(ctx->d_out);
+        ctx->d_out = nullptr;
+        ctx->d_out_bytes = 0;
+        CUDA_TRY(cudaMalloc(&ctx->d_out, rgb_bytes));
+        ctx->d_out_bytes = rgb_bytes;
+    }
+    if (rgb8_bytes > ctx->d_out8_bytes) {
+        if (ctx->d_out8) cudaFree(ctx->d_out8);
+        ctx->d_out8 = nullptr;
+        ctx->d_out8_bytes = 0;
+        CUDA_TRY(cudaMalloc(&ctx->d_out8, rgb8_bytes));
+        ctx->d_out8_bytes = rgb8_bytes;
+    }
+    return RTGPU_OK;
+}
+
+// Issue (do not wait for) everything one device does for a host-buffer render: kernel + D2H of its
+// row bands into the full-frame host buffers.
+int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rtgpu_opts* opts, const rtgpu_rows* rows,
+                        void* out_rgb, uint8_t* out_rgb8) {
+    uint32_t precision, max_depth;
+    int st = check_opts(opts, &precision, &max_depth);
+    if (st != RTGPU_OK) return st;
+    RowSel sel;
+    st = normalise_rows(rows, camera->vsize, &sel);
+    if (st != RTGPU_OK) return st;
+    const uint32_t n_rows = count_rows(sel, camera->vsize);
+    const size_t elem = precision == RTGPU_PRECISION_F64 ? sizeof(double) : sizeof(float);
+    const size_t row_rgb = (size_t)camera->hsize * 3 * elem;
+    const size_t row_rgb8 = (size_t)camera->hsize * 3;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    st = ensure_out_buffers(ctx, out_rgb ? row_rgb * n_rows : 0, out_rgb8 ? row_rgb8 * n_rows : 0);
+    if (st != RTGPU_OK) return st;
+    CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, rt::NUM_COUNTERS * sizeof(unsigned long long), ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    st = render_device_impl(ctx, camera, opts, rows, out_rgb ? ctx->d_out : nullptr, out_rgb8 ? ctx->d_out8 : nullptr,
+                            reinterpret_cast<uint64_t*>(ctx->d_counters), ctx->stream, nullptr);
+    if (st != RTGPU_OK) return st;
+    CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    // compact band b (rows [b*band_rows, ...)) of this shard -> image rows of band (b*shard_count + shard_index)
+    for (uint32_t k = 0; k < n_rows; k += sel.band_rows) {
+        const uint32_t rows_here = std::min(sel.band_rows, n_rows - k);
+        const uint32_t y = ((k / sel.band_rows) * sel.shard_count + sel.shard_index) * sel.band_rows;
+        if (out_rgb)
+            CUDA_TRY(cudaMemcpyAsync((char*)out_rgb + (size_t)y * row_rgb, (char*)ctx->d_out + (size_t)k * row_rgb,
+                                     row_rgb * rows_here, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_rgb8)
+            CUDA_TRY(cudaMemcpyAsync(out_rgb8 + (size_t)y * row_rgb8, ctx->d_out8 + (size_t)k * row_rgb8, row_rgb8 * rows_here,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return RTGPU_OK;
+}
+
+int finish_host_render(rtgpu_context* ctx, rtgpu_stats* stats) {
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (stats) {
+        unsigned long long c[rt::NUM_COUNTERS];
+        CUDA_TRY(cudaMemcpy(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+        stats->rays_primary += c[rt::COUNTER_PRIMARY];
+        stats->rays_shadow += c[rt::COUNTER_SHADOW];
+        stats->rays_reflect += c[rt::COUNTER_REFLECT];
+        stats->rays_refract += c[rt::COUNTER_REFRACT];
+        stats->hit_nodes += c[rt::COUNTER_HIT_NODES];
+        stats->pixels += c[rt::COUNTER_PIXELS];
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        stats->kernel_ms = std::max(stats->kernel_ms, (double)ms);
+    }
+    return RTGPU_OK;
+}
+
+double wall_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// FMA-chain peak kernels: 8 independent chains per thread
+template <typename T>
+__global__ void fma_peak_kernel(T* out, int iters, T a, T b) {
+    T x0 = (T)threadIdx.x, x1 = x0 + T(1), x2 = x0 + T(2), x3 = x0 + T(3), x4 = x0 + T(4), x5 = x0 + T(5), x6 = x0 + T(6), x7 = x0 + T(7);
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b);
+        x1 = fma(x1, a, b);
+        x2 = fma(x2, a, b);
+        x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b);
+        x5 = fma(x5, a, b);
+        x6 = fma(x6, a, b);
+        x7 = fma(x7, a, b);
+    }
+    T s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == T(-12345.678)) out[0] = s;  // never true: keeps the chains alive
+}
+
+template <typename T>
+int measure_peak(int device, double* out_tflops, double* out_ms) {
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    T* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, sizeof(T)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
+    fma_peak_kernel<T><<<blocks, threads>>>(d, 1024, (T)0.999, (T)0.001);  // warm-up
+    double best = 1e30;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0));
+        fma_peak_kernel<T><<<blocks, threads>>>(d, iters, (T)0.999, (T)0.001);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, (double)ms);
+    }
+    CUDA_TRY(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    const double flops = 2.0 * 8.0 * (double)iters * (double)threads * (double)blocks;
+    if (out_tflops) *out_tflops = flops / (best * 1e-3) / 1e12;
+    if (out_ms) *out_ms = best;
+    return RTGPU_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+
+extern "C" {
+
+uint32_t rtgpu_abi_version(void) { return RTGPU_ABI_VERSION; }
+
+const char* rtgpu_last_error(void) { return g_last_error.c_str(); }
+
+int rtgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n < 0 ? 0 : n;
+}
+
+uint32_t rtgpu_rows_count(const rtgpu_rows* rows, uint32_t vsize) {
+    RowSel sel;
+    if (normalise_rows(rows, vsize, &sel) != RTGPU_OK) return 0;
+    return count_rows(sel, vsize);
+}
+
+uint32_t rtgpu_rows_list(const rtgpu_rows* rows, uint32_t vsize, uint32_t* out_rows, uint32_t capacity) {
+    RowSel sel;
+    if (normalise_rows(rows, vsize, &sel) != RTGPU_OK) return 0;
+    const uint32_t n = count_rows(sel, vsize);
+    if (out_rows)
+        for (uint32_t k = 0; k < n && k < capacity; ++k)
+            out_rows[k] = ((k / sel.band_rows) * sel.shard_count + sel.shard_index) * sel.band_rows + k % sel.band_rows;
+    return n;
+}
+
+int rtgpu_context_create(const rtgpu_scene* scene, int device, rtgpu_context** out_context) {
+    if (!out_context) return fail(RTGPU_ERR_INVALID_ARGUMENT, "out_context is NULL");
+    *out_context = nullptr;
+    PackedScene packed;
+    int st = pack_scene(scene, &packed);
+    if (st != RTGPU_OK) return st;
+    rtgpu_context* ctx = new rtgpu_context();
+    st = context_init(ctx, device);
+    if (st == RTGPU_OK) st = upload_scene(ctx, packed);
+    if (st != RTGPU_OK) {
+        std::string keep = g_last_error;
+        context_release(ctx);
+        g_last_error = keep;
+        return st;
+    }
+    *out_context = ctx;
+    return RTGPU_OK;
+}
+
+void rtgpu_context_destroy(rtgpu_context* context) { context_release(context); }
+
+int rtgpu_context_render_device(rtgpu_context* context, const rtgpu_camera* camera, const rtgpu_opts* opts,
+                                const rtgpu_rows* rows, void* d_out_rgb, uint8_t* d_out_rgb8, uint64_t* d_counters,
+                                void* cuda_stream) {
+    return render_device_impl(context, camera, opts, rows, d_out_rgb, d_out_rgb8, d_counters, (cudaStream_t)cuda_stream, nullptr);
+}
+
+int rtgpu_context_render(rtgpu_context* context, const rtgpu_camera* camera, const rtgpu_opts* opts, const rtgpu_rows* rows,
+                         double* out_rgb, uint8_t* out_rgb8, rtgpu_stats* stats) {
+    if (!context || !camera) return fail(RTGPU_ERR_INVALID_ARGUMENT, "context or camera is NULL");
+    if (!out_rgb && !out_rgb8) return fail(RTGPU_ERR_INVALID_ARGUMENT, "both output pointers are NULL");
+    const double t0 = wall_ms();
+    if (stats) memset(stats, 0, sizeof(*stats));
+    int st = enqueue_host_render(context, camera, opts, rows, out_rgb, out_rgb8);
+    if (st != RTGPU_OK) return st;
+    st = finish_host_render(context, stats);
+    if (st != RTGPU_OK) return st;
+    if (stats) stats->total_ms = wall_ms() - t0;
+    return RTGPU_OK;
+}
+
+int rtgpu_render(const rtgpu_scene* scene, const rtgpu_camera* camera, const rtgpu_opts* opts, double* out_rgb,
+                 uint8_t* out_rgb8, rtgpu_stats* stats) {
+    if (!camera) return fail(RTGPU_ERR_INVALID_ARGUMENT, "camera is NULL");
+    if (!out_rgb && !out_rgb8) return fail(RTGPU_ERR_INVALID_ARGUMENT, "both output pointers are NULL");
+    const double t0 = wall_ms();
+    if (stats) memset(stats, 0, sizeof(*stats));
+    PackedScene packed;
+    int st = pack_scene(scene, &packed);
+    if (st != RTGPU_OK) return st;
+    const int available = rtgpu_device_count();
+    if (available <= 0) return fail(RTGPU_ERR_NO_DEVICE, "no CUDA device available (gpu mode has no CPU fallback)");
+    int n_gpus = (opts && opts->n_gpus > 0) ? opts->n_gpus : 1;
+    if (n_gpus > available) return fail(RTGPU_ERR_INVALID_ARGUMENT, "opts.n_gpus %d > %d visible devices", n_gpus, available);
+    uint32_t band_rows = (opts && opts->band_rows) ? opts->band_rows : 16u;
+    band_rows = (band_rows + 3u) & ~3u;  // whole 8x4 tiles per band
+
+    // One resident scene per device, kept for the lifetime of the process so that repeated frames
+    // pay for the upload but not for cudaMalloc / stream creation.
+    static std::mutex mu;
+    static std::vector<rtgpu_context*> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    if ((int)cache.size() < n_gpus) cache.resize(n_gpus, nullptr);
+    for (int g = 0; g < n_gpus; ++g) {
+        if (!cache[g]) {
+            rtgpu_context* ctx = new rtgpu_context();
+            st = context_init(ctx, g);
+            if (st != RTGPU_OK) {
+                std::string keep = g_last_error;
+                context_release(ctx);
+                g_last_error = keep;
+                return st;
+            }
+            cache[g] = ctx;
+        }
+        CUDA_TRY(cudaSetDevice(g));
+        st = upload_scene(cache[g], packed);
+        if (st != RTGPU_OK) return st;
+    }
+    // row bands: device g renders bands g, g+G, g+2G, ... (interleaved: per-row cost varies a lot)
+    for (int g = 0; g < n_gpus; ++g) {
+        rtgpu_rows rows;
+        rows.band_rows = n_gpus == 1 ? 0u : band_rows;
+        rows.shard_index = (uint32_t)g;
+        rows.shard_count = (uint32_t)n_gpus;
+        st = enqueue_host_render(cache[g], camera, opts, &rows, out_rgb, out_rgb8);
+        if (st != RTGPU_OK) return st;
+    }
+    for (int g = 0; g < n_gpus; ++g) {
+        st = finish_host_render(cache[g], stats);
+        if (st != RTGPU_OK) return st;
+    }
+    if (stats) stats->total_ms = wall_ms() - t0;
+    return RTGPU_OK;
+}
+
+int rtgpu_measure_fma_peak(int device, uint32_t precision, double* out_tflops, double* out_ms) {
+    if (rtgpu_device_count() <= 0) return fail(RTGPU_ERR_NO_DEVICE, "no CUDA device available");
+    if (precision == RTGPU_PRECISION_F64) return measure_peak<double>(device, out_tflops, out_ms);
+    if (precision == RTGPU_PRECISION_F32) return measure_peak<float>(device, out_tflops, out_ms);
+    return fail(RTGPU_ERR_INVALID_ARGUMENT, "precision %u", precision);
+}
+
+}  // extern "C"

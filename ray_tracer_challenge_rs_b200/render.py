@@ -1,0 +1,169 @@
+"""``Camera.render_gpu`` and the resident-scene renderer: thin callers of the C ABI (include/rtgpu.h).
+
+Nothing here computes pixels.  If ``librtgpu.so`` is missing, or there is no CUDA device, every
+entry point raises — the gpu rendering mode has no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple, Union
+
+import numpy as np
+
+from . import abi
+from .flatten import FlatScene, camera_to_c, flatten_world
+from .scene import Camera, Canvas, World
+
+SceneLike = Union[World, FlatScene]
+
+
+def _flat(scene: SceneLike) -> FlatScene:
+    return scene if isinstance(scene, FlatScene) else flatten_world(scene)
+
+
+def _opts(precision: str = "f64", max_depth: int = World.MAX_REFLECTION_ITERATIONS, n_gpus: int = 1, band_rows: int = 16) -> abi.RtgpuOpts:
+    prec = {"f64": abi.PRECISION_F64, "f32": abi.PRECISION_F32}[precision]
+    return abi.RtgpuOpts(prec, int(max_depth), int(n_gpus), int(band_rows), 0)
+
+
+def device_count() -> int:
+    return int(abi.load_library().rtgpu_device_count())
+
+
+def render_gpu(
+    camera: Camera,
+    world: SceneLike,
+    precision: str = "f64",
+    max_depth: int = World.MAX_REFLECTION_ITERATIONS,
+    n_gpus: int = 1,
+    band_rows: int = 16,
+    want_rgb: bool = True,
+    want_rgb8: bool = True,
+    return_stats: bool = False,
+):
+    """One-shot render through ``rtgpu_render`` (the call a ``RenderingMode::Gpu`` arm makes).
+
+    Returns a :class:`Canvas` whose ``pixels`` are the linear colours (f64; f32 in fast mode) and
+    whose ``to_rgb8()`` are the bytes the device quantised (canvas.rs:117-123)."""
+    lib = abi.load_library()
+    flat = _flat(world)
+    cscene = flat.as_c()
+    ccam = camera_to_c(camera)
+    n = camera.horizontal_size * camera.vertical_size
+    dtype = np.float64 if precision == "f64" else np.float32
+    rgb = np.zeros((n, 3), dtype) if want_rgb else None
+    rgb8 = np.zeros((n, 3), np.uint8) if want_rgb8 else None
+    stats = abi.RtgpuStats()
+    opts = _opts(precision, max_depth, n_gpus, band_rows)
+    st = lib.rtgpu_render(
+        C.byref(cscene),
+        C.byref(ccam),
+        C.byref(opts),
+        rgb.ctypes.data if rgb is not None else None,
+        rgb8.ctypes.data if rgb8 is not None else None,
+        C.byref(stats),
+    )
+    abi.check(lib, st)
+    canvas = Canvas(camera.horizontal_size, camera.vertical_size, rgb if rgb is not None else np.zeros((n, 3)), rgb8)
+    if return_stats:
+        return canvas, stats.as_dict()
+    return canvas
+
+
+class Renderer:
+    """A scene resident on one device (``rtgpu_context``): what a caller rendering many frames, or
+    one rank of a row-band-sharded job, uses."""
+
+    def __init__(self, world: SceneLike, device: int = 0):
+        self._lib = abi.load_library()
+        self.flat = _flat(world)
+        self._cscene = self.flat.as_c()
+        self._ctx = C.c_void_p()
+        self.device = device
+        abi.check(self._lib, self._lib.rtgpu_context_create(C.byref(self._cscene), device, C.byref(self._ctx)))
+
+    def close(self) -> None:
+        if self._ctx:
+            self._lib.rtgpu_context_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def rows_count(self, camera: Camera, rows: Optional[Tuple[int, int, int]]) -> int:
+        r = abi.RtgpuRows(*(rows or (0, 0, 1)))
+        return int(self._lib.rtgpu_rows_count(C.byref(r), camera.vertical_size))
+
+    def render(
+        self,
+        camera: Camera,
+        precision: str = "f64",
+        max_depth: int = World.MAX_REFLECTION_ITERATIONS,
+        rows: Optional[Tuple[int, int, int]] = None,
+        out_rgb: Optional[np.ndarray] = None,
+        out_rgb8: Optional[np.ndarray] = None,
+        want_rgb: bool = True,
+        want_rgb8: bool = True,
+    ):
+        """Host buffers in, host buffers out (``rtgpu_context_render``): full-frame arrays; only the
+        rows that ``rows = (band_rows, shard_index, shard_count)`` selects are written."""
+        n = camera.horizontal_size * camera.vertical_size
+        dtype = np.float64 if precision == "f64" else np.float32
+        if out_rgb is None and want_rgb:
+            out_rgb = np.zeros((n, 3), dtype)
+        if out_rgb8 is None and want_rgb8:
+            out_rgb8 = np.zeros((n, 3), np.uint8)
+        ccam = camera_to_c(camera)
+        opts = _opts(precision, max_depth)
+        r = abi.RtgpuRows(*(rows or (0, 0, 1)))
+        stats = abi.RtgpuStats()
+        st = self._lib.rtgpu_context_render(
+            self._ctx,
+            C.byref(ccam),
+            C.byref(opts),
+            C.byref(r),
+            out_rgb.ctypes.data if out_rgb is not None else None,
+            out_rgb8.ctypes.data if out_rgb8 is not None else None,
+            C.byref(stats),
+        )
+        abi.check(self._lib, st)
+        return out_rgb, out_rgb8, stats.as_dict()
+
+    def render_device(
+        self,
+        camera: Camera,
+        d_out_rgb: int,
+        d_out_rgb8: int,
+        d_counters: int,
+        stream: int,
+        precision: str = "f64",
+        max_depth: int = World.MAX_REFLECTION_ITERATIONS,
+        rows: Optional[Tuple[int, int, int]] = None,
+    ) -> None:
+        """Asynchronous launch on device pointers and a caller-owned stream
+        (``rtgpu_context_render_device``); outputs are compact over the selected rows."""
+        ccam = camera_to_c(camera)
+        opts = _opts(precision, max_depth)
+        r = abi.RtgpuRows(*(rows or (0, 0, 1)))
+        st = self._lib.rtgpu_context_render_device(
+            self._ctx, C.byref(ccam), C.byref(opts), C.byref(r), d_out_rgb or None, d_out_rgb8 or None, d_counters or None, stream or None
+        )
+        abi.check(self._lib, st)
+
+
+def measure_fma_peak(precision: str = "f64", device: int = 0) -> Tuple[float, float]:
+    """(TFLOP/s, ms) of a dependent-free FMA chain on every SM — the FP-pipe roofline denominator."""
+    lib = abi.load_library()
+    tf, ms = C.c_double(), C.c_double()
+    prec = {"f64": abi.PRECISION_F64, "f32": abi.PRECISION_F32}[precision]
+    abi.check(lib, lib.rtgpu_measure_fma_peak(device, prec, C.byref(tf), C.byref(ms)))
+    return tf.value, ms.value

@@ -1,0 +1,147 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star):
+  * f64 parity mode: 8-bit output within +-1 LSB on >= 99.9 % of pixels, every mismatch listed.
+    What we actually assert is much tighter: RGB8 byte-identical, the f64 buffer equal except for
+    the few pixels where CUDA's pow() and glibc's differ in the last bits (material.rs:110 is the
+    only transcendental on the path), ray counters integer-equal.
+  * shard / multi-GPU: N row-band shards == the unsharded frame, byte for byte.
+  * at the reference's native sizes: sha256 of the GPU RGB8 frame == sha256 of the reference's PNG.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from ray_tracer_challenge_rs_b200.fixtures import SHIPPED_SCENES, load_scene_fixture
+from ray_tracer_challenge_rs_b200.render import Renderer, device_count, render_gpu
+
+from worlds import SPECIAL_WORLDS
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+with open(os.path.join(GOLDEN, "golden_index.json")) as f:
+    INDEX = json.load(f)
+
+COUNTERS = ("rays_primary", "rays_shadow", "rays_reflect", "rays_refract", "hit_nodes", "pixels")
+F64_RTOL = 1e-12  # pow() ulp noise only; anything structural is orders of magnitude larger
+
+
+def compare_with_oracle(flat, camera, max_depth=6, label=""):
+    canvas, gstats = render_gpu(camera, flat, max_depth=max_depth, return_stats=True)
+    rgb, rgb8, ostats = Oracle(flat).render(camera, max_depth=max_depth, threads=0)
+    g8 = canvas.to_rgb8().reshape(-1, 3)
+    w = camera.horizontal_size
+    # 1. bytes
+    bad8 = np.argwhere((g8 != rgb8).any(axis=1)).ravel()
+    listing = [(int(i % w), int(i // w), g8[i].tolist(), rgb8[i].tolist()) for i in bad8[:20]]
+    assert bad8.size == 0, f"{label}: {bad8.size} RGB8 mismatches (x, y, gpu, oracle): {listing}"
+    # 2. f64 colours
+    diff = np.abs(canvas.pixels - rgb)
+    scale = np.maximum(np.abs(rgb), 1.0)
+    worst = float((diff / scale).max()) if diff.size else 0.0
+    assert worst <= F64_RTOL, f"{label}: max relative f64 error {worst:.3e}"
+    # 3. work counters
+    for k in COUNTERS:
+        assert gstats[k] == ostats[k], (label, k, gstats[k], ostats[k])
+    n_differ = int((canvas.pixels != rgb).any(axis=1).sum())
+    return n_differ, worst
+
+
+@pytest.mark.parametrize("name", SHIPPED_SCENES)
+def test_shipped_scene_small(name):
+    flat, camera = load_scene_fixture(name)
+    cam = camera.resized(384, 384 * camera.vertical_size // camera.horizontal_size)
+    n_differ, worst = compare_with_oracle(flat, cam, label=name)
+    print(f"{name}: {n_differ} pixels differ in f64 (max rel {worst:.2e})")
+
+
+@pytest.mark.parametrize("name", sorted(SPECIAL_WORLDS))
+def test_special_world(name):
+    world, camera = SPECIAL_WORLDS[name]()
+    compare_with_oracle(world.flatten(), camera, label=name)
+
+
+@pytest.mark.parametrize("max_depth", [0, 1, 3, 5, 7, 9])
+def test_recursion_depths(max_depth):
+    flat, camera = load_scene_fixture("refraction")
+    compare_with_oracle(flat, camera.resized(96, 96), max_depth=max_depth, label=f"refraction@{max_depth}")
+    world, camera = SPECIAL_WORLDS["mirror_box"]()
+    compare_with_oracle(world.flatten(), camera, max_depth=max_depth, label=f"mirror_box@{max_depth}")
+
+
+@pytest.mark.parametrize("size", [(1, 1), (7, 5), (33, 17), (130, 3), (3, 130)])
+def test_ragged_sizes(size):
+    flat, camera = load_scene_fixture("cover")
+    compare_with_oracle(flat, camera.resized(*size), label=f"cover@{size}")
+
+
+@pytest.mark.parametrize("name", SHIPPED_SCENES)
+def test_native_size_matches_reference_png(name):
+    """GPU render at the reference's native camera size == the reference's own PNG, byte for byte."""
+    flat, camera = load_scene_fixture(name)
+    meta = INDEX[name]
+    canvas = render_gpu(camera, flat, want_rgb=False)
+    frame = canvas.to_rgb8()
+    with np.load(os.path.join(GOLDEN, f"{name}.rows.npz")) as z:
+        rows, golden_rows = z["rows"], z["rgb8"]
+    bad = np.argwhere((frame[rows] != golden_rows).any(axis=2))
+    assert bad.shape[0] == 0, f"{name}: {bad.shape[0]} mismatching sampled pixels, first (row, x): {[(int(rows[r]), int(x)) for r, x in bad[:10]]}"
+    assert hashlib.sha256(np.ascontiguousarray(frame).tobytes()).hexdigest() == meta["sha256_rgb8"]
+
+
+def test_cover_1080p_against_oracle():
+    """BASELINE.json config 2: cover.yaml at 1920x1080, f64 parity mode vs the CPU image."""
+    flat, camera = load_scene_fixture("cover")
+    n_differ, worst = compare_with_oracle(flat, camera.resized(1920, 1080), label="cover@1080p")
+    print(f"cover@1080p: {n_differ} pixels differ in f64 (max rel {worst:.2e})")
+
+
+@pytest.mark.parametrize("band,count", [(16, 2), (16, 4), (4, 8), (5, 3)])
+def test_row_band_shards_equal_whole_frame(band, count):
+    """What N GPUs would each render (rtgpu_rows) assembles to exactly the unsharded frame."""
+    flat, camera = load_scene_fixture("reflect_refract")
+    cam = camera.resized(320, 214)
+    with Renderer(flat) as r:
+        whole, whole8, wstats = r.render(cam)
+        rgb = np.full_like(whole, np.nan)
+        rgb8 = np.zeros_like(whole8)
+        totals = dict.fromkeys(COUNTERS, 0)
+        for index in range(count):
+            _, _, st = r.render(cam, rows=(band, index, count), out_rgb=rgb, out_rgb8=rgb8)
+            for k in COUNTERS:
+                totals[k] += st[k]
+    assert np.array_equal(rgb.view(np.uint64), whole.view(np.uint64))
+    assert np.array_equal(rgb8, whole8)
+    assert totals == {k: wstats[k] for k in COUNTERS}
+
+
+def test_multi_gpu_one_shot_is_byte_identical():
+    n = device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    flat, camera = load_scene_fixture("cover")
+    cam = camera.resized(640, 360)
+    one = render_gpu(cam, flat, n_gpus=1)
+    for g in sorted({2, min(n, 4), n}):
+        many = render_gpu(cam, flat, n_gpus=g, band_rows=8)
+        assert np.array_equal(many.pixels.view(np.uint64), one.pixels.view(np.uint64)), g
+        assert np.array_equal(many.to_rgb8(), one.to_rgb8()), g
+
+
+def test_f32_fast_mode_tolerance():
+    """f32 fast mode: own offset epsilon, stated tolerance: >= 99 % of pixels within 2 LSB of the f64
+    oracle on scenes without refraction chains; reported, and bounded loosely, elsewhere."""
+    for name, frac_bar in (("three_sphere_scene", 0.995), ("shadow_puppets", 0.995), ("metal", 0.99), ("cover", 0.97)):
+        flat, camera = load_scene_fixture(name)
+        cam = camera.resized(384, 384 * camera.vertical_size // camera.horizontal_size)
+        canvas = render_gpu(cam, flat, precision="f32")
+        _, rgb8, _ = Oracle(flat).render(cam, want_rgb=False)
+        d = np.abs(canvas.to_rgb8().reshape(-1, 3).astype(int) - rgb8.astype(int)).max(axis=1)
+        frac = float((d <= 2).mean())
+        print(f"f32 {name}: {frac * 100:.3f}% within 2 LSB, max {int(d.max())}")
+        assert frac >= frac_bar, (name, frac)
