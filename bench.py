@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — the camera render pass on N B200s of one node, beside the CPU reference arm.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--scene cover] [--width 1920] [--height 1080] [--precision f64] [--max-depth 6]
+
+A "step" = one full frame of the workload (default: BASELINE.json configs[1], the reference's
+cover scene at 1920x1080, f64 parity mode, recursion depth 6).  Prints ONE JSON line:
+
+  value        Mrays/s with everything resident on the device: the render kernel(s) only, CUDA events
+               on the launching stream, summed over exactly K steps, max over ranks.  Rays =
+               World::collect_intersections calls (primary + shadow + reflect + refract), counted on
+               the device and integer-equal to the CPU oracle's count.
+  e2e          the same metric through the reference-facing call rtgpu_render() (scene pack + H2D,
+               kernel on N devices in row bands, D2H of the f64 Canvas into pinned host memory).
+  roofline     FP64 (or FP32) FMA-pipe roofline of the render kernel: algorithmic flops per frame
+               (SURVEY.md 8d table x device ray counters) / kernel time, against an FMA-chain peak
+               measured live in this run (MEASURED_PEAKS.json has no FP64/FP32 entry).
+  cpu_baseline the CPU oracle (restated reference, C + OpenMP, all host threads) on the same frame.
+
+`--impl reference` times that CPU arm alone (the reference is Rust and cannot be built in this
+image: the oracle port, validated byte-for-byte against the reference's golden renders, stands in).
+Under torchrun (N > 1) every rank renders its own interleaved row bands; no collective touches the
+data path — torch.distributed only carries the barrier and the max-over-ranks of the timings.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# algorithmic flops per ray-shape test (object-space transform + local_intersect,
+# hit-path upper bound) and per hit node.
+FLOP_PER_TEST = {"sphere": 60, "plane": 35, "cube": 45, "cylinder_open": 58, "cylinder_closed": 76,
+                 "cone_open": 63, "cone_closed": 83, "triangle": 78}
+FLOP_PER_HIT_NODE = 250
+FLOP_PER_HIT_NODE_PER_LIGHT = 100
+METRIC = "Mrays/s (primary+shadow+secondary)"
+
+
+def flops_per_ray(flat) -> int:
+    from ray_tracer_challenge_rs_b200 import abi
+
+    total = 0
+    for t, closed in zip(flat.shape_type.tolist(), flat.shape_closed.tolist()):
+        if t == abi.SPHERE:
+            total += FLOP_PER_TEST["sphere"]
+        elif t == abi.PLANE:
+            total += FLOP_PER_TEST["plane"]
+        elif t == abi.CUBE:
+            total += FLOP_PER_TEST["cube"]
+        elif t == abi.CYLINDER:
+            total += FLOP_PER_TEST["cylinder_closed" if closed else "cylinder_open"]
+        elif t == abi.CONE:
+            total += FLOP_PER_TEST["cone_closed" if closed else "cone_open"]
+        else:
+            total += FLOP_PER_TEST["triangle"]
+    return total
+
+
+def frame_flops(flat, stats) -> float:
+    rays = stats["rays_primary"] + stats["rays_shadow"] + stats["rays_reflect"] + stats["rays_refract"]
+    return float(rays) * flops_per_ray(flat) + float(stats["hit_nodes"]) * (FLOP_PER_HIT_NODE + FLOP_PER_HIT_NODE_PER_LIGHT * flat.n_lights)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.device_index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                mx.append(float(s[2]))
+                for name, v in zip(names, s[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_workload(args):
+    from ray_tracer_challenge_rs_b200.fixtures import load_scene_fixture
+
+    flat, camera = load_scene_fixture(args.scene)
+    return flat, camera.resized(args.width, args.height)
+
+
+def workload_config(args, flat, extra=None) -> dict:
+    cfg = {
+        "workload": f"{args.scene}.yaml @ {args.width}x{args.height}, {args.precision} {'parity' if args.precision == 'f64' else 'fast'} mode, "
+                    f"max recursion depth {args.max_depth} (BASELINE.json configs[1])",
+        "scene": args.scene, "width": args.width, "height": args.height, "precision": args.precision,
+        "max_depth": args.max_depth, "shapes": flat.shape_counts(), "lights": flat.n_lights,
+        "cache": "scene tables are ~3 KB staged in shared memory and the 50 MB frame is write-only, so L2 contents cannot help a step; "
+                 "a 256 MiB buffer is overwritten between timed steps anyway (L2 flush, outside the event pairs)",
+    }
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the CPU oracle on all host threads
+
+
+def time_oracle(flat, camera, max_depth: int, steps: int, warmup: int, threads: int = 0):
+    from oracle import oracle as O
+
+    orc = O.Oracle(flat)
+    n = camera.horizontal_size * camera.vertical_size
+    from ray_tracer_challenge_rs_b200 import abi
+    from ray_tracer_challenge_rs_b200.flatten import camera_to_c
+    import ctypes as C
+
+    cam = camera_to_c(camera)
+    rgb = np.zeros((n, 3), np.float64)
+    lib = O.lib()
+    stats = abi.RtgpuStats()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        st = lib.rto_render(C.byref(orc._c), C.byref(cam), max_depth, None, threads, rgb.ctypes.data, None, C.byref(stats))
+        t1 = time.perf_counter()
+        assert st == 0
+        if i >= warmup:
+            times.append(t1 - t0)
+    return times, stats.as_dict(), (O.max_threads() if threads <= 0 else threads)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the CPU arm runs once, on rank 0
+    flat, camera = load_workload(args)
+    times, stats, cores = time_oracle(flat, camera, args.max_depth, args.steps, args.warmup)
+    total = sum(times)
+    mrays = stats["rays"] * len(times) / total / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic: the reference's cover scene (committed flattened fixture), camera resized",
+        "config": workload_config(args, flat),
+        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                         "sample": f"the whole {args.width}x{args.height} frame, {len(times)} times; restated reference (C + OpenMP, "
+                                   "-ffp-contract=off), not rustc output — no Rust toolchain in this image",
+                         "ms_per_frame": total / len(times) * 1e3, "best_ms_per_frame": min(times) * 1e3},
+        "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "rays_per_frame": stats["rays"],
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from ray_tracer_challenge_rs_b200 import abi
+    from ray_tracer_challenge_rs_b200.render import Renderer, measure_fma_peak, render_gpu
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(xs):
+        t = torch.tensor(xs, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
+    flat, camera = load_workload(args)
+    K, W = args.steps, max(args.warmup, 0)
+    elem = 8 if args.precision == "f64" else 4
+    tdtype = torch.float64 if args.precision == "f64" else torch.float32
+    rows = (16, rank, world) if world > 1 else None
+
+    renderer = Renderer(flat, device=local_rank)
+    my_rows = renderer.rows_count(camera, rows)
+    d_out = torch.empty((max(my_rows, 1) * camera.horizontal_size, 3), dtype=tdtype, device="cuda")
+    d_counters = torch.zeros(6, dtype=torch.int64, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def launch():
+        renderer.render_device(camera, d_out.data_ptr(), 0, d_counters.data_ptr(), stream.cuda_stream, precision=args.precision,
+                               max_depth=args.max_depth, rows=rows)
+
+    # ---- device-resident timing ("value") ----
+    for _ in range(W):
+        launch()
+    barrier()
+    d_counters.zero_()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        t_wall0 = time.perf_counter()
+        for i in range(K):
+            flush.fill_(i & 0xFF)  # L2 flush between timed steps (outside the event pair)
+            starts[i].record(stream)
+            launch()
+            ends[i].record(stream)
+        barrier()
+        t_wall1 = time.perf_counter()
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    device_ms = max_over_ranks(sum(step_ms))
+    counters = [int(v) // K for v in sum_over_ranks([float(v) for v in d_counters.tolist()])]
+    stats = dict(zip(("rays_primary", "rays_shadow", "rays_reflect", "rays_refract", "hit_nodes", "pixels"), counters))
+    rays = stats["rays_primary"] + stats["rays_shadow"] + stats["rays_reflect"] + stats["rays_refract"]
+    value = rays * K / (device_ms * 1e-3) / 1e6
+    clock_summary = clocks.summary()
+
+    # ---- end to end through the reference-facing call, host buffers (rank 0 drives all N devices) ----
+    n_px = camera.horizontal_size * camera.vertical_size
+    e2e = None
+    if rank == 0:
+        host = torch.empty((n_px, 3), dtype=tdtype).pin_memory()
+        host_np = host.numpy()
+        lib = abi.load_library()
+        import ctypes as C
+        from ray_tracer_challenge_rs_b200.flatten import camera_to_c
+
+        cscene, ccam = flat.as_c(), camera_to_c(camera)
+        opts = abi.RtgpuOpts(abi.PRECISION_F64 if args.precision == "f64" else abi.PRECISION_F32, args.max_depth, world, 16, 0)
+        st = abi.RtgpuStats()
+
+        def one_frame():
+            abi.check(lib, lib.rtgpu_render(C.byref(cscene), C.byref(ccam), C.byref(opts), host_np.ctypes.data, None, C.byref(st)))
+
+    if world > 1:
+        renderer.close()  # rank 0's one-shot call owns every device for the e2e leg
+    barrier()
+    if rank == 0:
+        for _ in range(W):
+            one_frame()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            one_frame()
+        t1 = time.perf_counter()
+        e2e_ms = (t1 - t0) * 1e3 / K
+        scene_bytes = int(flat.n_shapes * 16 * 8 + flat.n_triangles * 12 * 8 + flat.n_materials * 12 * 8 + flat.n_patterns * 18 * 8 +
+                          flat.n_lights * 6 * 8 + flat.n_shapes * 16 + flat.n_materials * 8 + flat.n_patterns * 16)
+        e2e = {"value": st.as_dict()["rays"] / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": e2e_ms,
+               "h2d_bytes_per_step": scene_bytes * world + 256 * world, "d2h_bytes_per_step": n_px * 3 * elem + 48 * world,
+               "call": "rtgpu_render (scene pack + upload, kernel on N devices in 16-row bands, D2H of the full f64 Canvas into pinned host memory)",
+               "kernel_ms_max_over_devices": st.kernel_ms}
+        assert st.as_dict()["rays"] == rays, (st.as_dict(), stats)
+    barrier()
+
+    if rank == 0:
+        # ---- roofline of the render kernel: FP-pipe ----
+        peak_tflops, _ = measure_fma_peak(args.precision, device=local_rank)
+        flops = frame_flops(flat, stats)  # whole frame, all ranks
+        achieved = flops / world / (device_ms / K * 1e-3) / 1e12  # per device: each renders 1/N of the frame in device_ms/K
+        roofline = {
+            "bound": "fp64_fma_pipe" if args.precision == "f64" else "fp32_fma_pipe", "achieved": achieved, "peak": peak_tflops,
+            "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": None,
+            "peak_source": "measured live: 8 independent FMA chains per thread on every SM (rtgpu_measure_fma_peak); "
+                           "MEASURED_PEAKS.json holds only HBM and bf16 peaks",
+            "algorithmic_flops_per_frame": flops, "flops_per_ray": flops_per_ray(flat),
+            "hbm_note": f"frame write {n_px * 3 * elem / 1e6:.1f} MB per step = "
+                        f"{n_px * 3 * elem / (device_ms / K * 1e-3) / 1e9 / world:.1f} GB/s per device: HBM is not the bound",
+        }
+        # ---- CPU baseline beside it (bounded: 3 frames) ----
+        times, ostats, cores = time_oracle(flat, camera, args.max_depth, steps=3, warmup=1)
+        assert ostats["rays"] == rays, (ostats, stats)
+        cpu = {"value": ostats["rays"] / min(times) / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+               "sample": f"the same whole {args.width}x{args.height} frame, best of 3; restated reference (C + OpenMP), not rustc output",
+               "ms_per_frame": min(times) * 1e3}
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": device_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic: the reference's cover scene (committed flattened fixture), camera resized to 1920x1080",
+            "config": workload_config(args, flat, {"parallelism": f"row bands of 16 rows, interleaved over {world} GPU(s); no collective in the data path"}),
+            "e2e": e2e, "gpu_launches": 2 * K * world, "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_summary,
+            "rays_per_frame": rays, "ms_per_frame": device_ms / K, "wall_ms_per_step_incl_flush": (t_wall1 - t_wall0) * 1e3 / K,
+            "counters": stats,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scene", default="cover")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--max-depth", type=int, default=6)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
