@@ -231,6 +231,13 @@ int rtgpu_context_render(rtgpu_context *context, const rtgpu_camera *camera, con
  * Returns TFLOP/s (2 flop per fma) in *out_tflops; runs on `device`, on `cuda_stream`. */
 int rtgpu_measure_fma_peak(int device, uint32_t precision, double *out_tflops, double *out_ms);
 
+/* Self-test of the IEEE-exact fast division / square root the FP64 kernels use (csrc/rt_arith.cuh):
+ * for every i < n evaluates a[i] / b[i] and sqrt(a[i]) with the restructured sequences and with
+ * the native operators on `device`, and counts bitwise differences where the fast path declared
+ * itself valid (must be 0) and how often it fell back to the native operator.  a, b: host arrays. */
+int rtgpu_selftest_arith(int device, const double *a, const double *b, size_t n, uint64_t *out_div_mismatches,
+                         uint64_t *out_sqrt_mismatches, uint64_t *out_div_fallbacks, uint64_t *out_sqrt_fallbacks);
+
 #ifdef __cplusplus
 }
 #endif

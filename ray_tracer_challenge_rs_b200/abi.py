@@ -131,6 +131,7 @@ EXPORTED_SYMBOLS = (
     "rtgpu_context_render_device",
     "rtgpu_context_render",
     "rtgpu_measure_fma_peak",
+    "rtgpu_selftest_arith",
 )
 
 PACKAGE_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -150,7 +151,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIBRARY_PATH
+    p = path or os.environ.get("RTGPU_LIBRARY") or LIBRARY_PATH  # RTGPU_LIBRARY: A/B builds of the same ABI
     if not os.path.exists(p):
         raise RuntimeError(
             f"{p} is missing: the CUDA library has not been built (run `python -c 'import "
@@ -203,6 +204,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     ]
     lib.rtgpu_measure_fma_peak.restype = C.c_int
     lib.rtgpu_measure_fma_peak.argtypes = [C.c_int, C.c_uint32, _pd, _pd]
+    lib.rtgpu_selftest_arith.restype = C.c_int
+    lib.rtgpu_selftest_arith.argtypes = [C.c_int, _pd, _pd, C.c_size_t, _pu64, _pu64, _pu64, _pu64]
     if lib.rtgpu_abi_version() != ABI_VERSION:
         raise RuntimeError(f"{p}: ABI version {lib.rtgpu_abi_version()} != {ABI_VERSION}")
     if path is None:

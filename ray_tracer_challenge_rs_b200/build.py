@@ -43,10 +43,14 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > out_m for d in deps)
 
 
-def build(force: bool = False, extra_flags: Optional[List[str]] = None, verbose: bool = False) -> str:
-    if not force and not _stale() and not extra_flags:
+def build(force: bool = False, extra_flags: Optional[List[str]] = None, verbose: bool = False, output: Optional[str] = None) -> str:
+    """Compile librtgpu.so.  `extra_flags` + `output` build an A/B variant next to it (select it at
+    run time with RTGPU_LIBRARY=<path>)."""
+    if not force and not _stale() and not extra_flags and output is None:
         return OUTPUT
-    cmd = [find_nvcc()] + NVCC_FLAGS + (extra_flags or []) + ["-I", INCLUDE, "-o", OUTPUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    output = output or OUTPUT
+    os.makedirs(os.path.dirname(output), exist_ok=True)
+    cmd = [find_nvcc()] + NVCC_FLAGS + (extra_flags or []) + ["-I", INCLUDE, "-o", output] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
@@ -58,7 +62,7 @@ def build(force: bool = False, extra_flags: Optional[List[str]] = None, verbose:
         print(log)
     if proc.returncode != 0:
         raise RuntimeError(f"nvcc failed ({proc.returncode}); see {os.path.join(PACKAGE_DIR, 'build.log')}")
-    return OUTPUT
+    return output
 
 
 if __name__ == "__main__":

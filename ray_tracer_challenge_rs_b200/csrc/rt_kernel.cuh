@@ -26,6 +26,7 @@
 #include <cfloat>
 #include <cstdint>
 
+#include "rt_arith.cuh"
 #include "rt_scene.h"
 
 namespace rt {
@@ -78,10 +79,21 @@ template <typename T> RT_DEV T dot(V3<T> a, V3<T> b) { return fma(a.z, b.z, fma(
 template <typename T> RT_DEV V3<T> cross(V3<T> a, V3<T> b) {
     return mk<T>(fma(a.y, b.z, -a.z * b.y), fma(a.z, b.x, -a.x * b.z), fma(a.x, b.y, -a.y * b.x));
 }
-// vector.rs:84-86
-template <typename T> RT_DEV T magnitude(V3<T> a) { return sqrt(sq(a.x) + sq(a.y) + sq(a.z)); }
-// vector.rs:88-91 (divides)
-template <typename T> RT_DEV V3<T> normalized(V3<T> a) { T m = magnitude(a); return mk<T>(a.x / m, a.y / m, a.z / m); }
+// vector.rs:84-91: magnitude = sqrt(x^2 + y^2 + z^2); normalized DIVIDES each component by it.
+// One exact sqrt + one shared reciprocal for the three exact quotients (rt_arith.cuh).
+template <typename T> RT_DEV V3<T> normalized(V3<T> a, T* magnitude_out = nullptr) {
+    bool ok = true;
+    T s = sq(a.x) + sq(a.y) + sq(a.z);
+    T m = sqrt_fast(s, ok);
+    Recip<T> r = recip(m, ok);
+    V3<T> q = mk<T>(quot0(a.x, r, ok), quot0(a.y, r, ok), quot0(a.z, r, ok));
+    if (!ok) {
+        m = sqrt(s);
+        q = mk<T>(a.x / m, a.y / m, a.z / m);
+    }
+    if (magnitude_out) *magnitude_out = m;
+    return q;
+}
 // vector.rs:105-107
 template <typename T> RT_DEV V3<T> reflect(V3<T> v, V3<T> n) { return v - ((n * T(2)) * dot(v, n)); }
 
@@ -225,13 +237,20 @@ RT_DEV bool solve_quadratic(T a, T b, T c, T& s1, T& s2) {
     T discriminant = fma(T(4) * a, -c, sq(b));
     if (discriminant < T(0)) return false;
     T double_a = T(2) * a;
-    T root = sqrt(discriminant);
-    s1 = (-b - root) / double_a;
-    s2 = (-b + root) / double_a;
+    bool ok = true;
+    T root = sqrt_fast(discriminant, ok);
+    Recip<T> r = recip(double_a, ok);
+    s1 = quot(-b - root, r, ok);
+    s2 = quot(-b + root, r, ok);
+    if (!ok) {
+        root = sqrt(discriminant);
+        s1 = (-b - root) / double_a;
+        s2 = (-b + root) / double_a;
+    }
     return true;
 }
 
-// shapes/cube.rs:22-43
+// shapes/cube.rs:22-43, native operators (fallback of cube_axis_fast)
 template <typename T>
 RT_DEV void cube_check_axis(T origin, T direction, T& tmin, T& tmax) {
     T nmin = T(-1) - origin;
@@ -253,12 +272,44 @@ RT_DEV void cube_check_axis(T origin, T direction, T& tmin, T& tmax) {
     tmax = dmax;
 }
 
+// shapes/cube.rs:22-43 without branches: both slab distances share one reciprocal; `ok` turns false
+// when an operand leaves the exact fast range AND the quotients are actually used.
+template <typename T>
+RT_DEV void cube_axis_fast(T origin, T direction, T& tmin, T& tmax, bool& ok) {
+    T nmin = T(-1) - origin;
+    T nmax = T(1) - origin;
+    const bool divide = fabs(direction) >= Real<T>::eps();
+    bool ok_div = true;
+    Recip<T> r = recip(direction, ok_div);
+    T qmin = quot(nmin, r, ok_div);
+    T qmax = quot(nmax, r, ok_div);
+    T dmin = divide ? qmin : nmin * Real<T>::max();
+    T dmax = divide ? qmax : nmax * Real<T>::max();
+    const bool swap = dmin > dmax;
+    tmin = swap ? dmax : dmin;
+    tmax = swap ? dmin : dmax;
+    ok = ok && (ok_div || !divide);
+}
+
 // cylinder.rs:34-39 / cone.rs:34-39 (radius 1 for the cylinder)
 template <typename T>
 RT_DEV bool check_cap(const Ray<T>& r, T distance, T radius_sq) {
     T x = fma(r.d.x, distance, r.o.x);
     T z = fma(r.d.z, distance, r.o.z);
     return (sq(x) + sq(z)) <= radius_sq;
+}
+
+// (min - o.y) / d.y and (max - o.y) / d.y of intersect_caps (cylinder.rs:47,52 / cone.rs:47,52)
+template <typename T>
+RT_DEV void cap_distances(T nlo, T nhi, T dy, T& dlo, T& dhi) {
+    bool ok = true;
+    Recip<T> r = recip(dy, ok);
+    dlo = quot(nlo, r, ok);
+    dhi = quot(nhi, r, ok);
+    if (!ok) {
+        dlo = nlo / dy;
+        dhi = nhi / dy;
+    }
 }
 
 // local_intersect of shape type TYPE on the object-space ray `r`; distances in push order.
@@ -278,14 +329,20 @@ RT_DEV int local_intersect(const Ray<T>& r, const T* g, int flags, const T* tri,
         }
     } else if (TYPE == 1) {  // shapes/plane.rs:42-48
         if (!(fabs(r.d.y) < Real<T>::eps())) {
-            ts[0] = -r.o.y / r.d.y;
+            ts[0] = div_exact(-r.o.y, r.d.y);
             n = 1;
         }
     } else if (TYPE == 2) {  // shapes/cube.rs:65-85
         T xmin, xmax, ymin, ymax, zmin, zmax;
-        cube_check_axis(r.o.x, r.d.x, xmin, xmax);
-        cube_check_axis(r.o.y, r.d.y, ymin, ymax);
-        cube_check_axis(r.o.z, r.d.z, zmin, zmax);
+        bool ok = true;
+        cube_axis_fast(r.o.x, r.d.x, xmin, xmax, ok);
+        cube_axis_fast(r.o.y, r.d.y, ymin, ymax, ok);
+        cube_axis_fast(r.o.z, r.d.z, zmin, zmax, ok);
+        if (!ok) {
+            cube_check_axis(r.o.x, r.d.x, xmin, xmax);
+            cube_check_axis(r.o.y, r.d.y, ymin, ymax);
+            cube_check_axis(r.o.z, r.d.z, zmin, zmax);
+        }
         T dmin = fmax(fmax(fmax(-Real<T>::max(), xmin), ymin), zmin);
         T dmax = fmin(fmin(fmin(Real<T>::max(), xmax), ymax), zmax);
         if (dmin < dmax && dmax > T(0)) {
@@ -313,10 +370,10 @@ RT_DEV int local_intersect(const Ray<T>& r, const T* g, int flags, const T* tri,
             }
         }
         if ((flags & FLAG_CLOSED) && !(fabs(r.d.y) < Real<T>::eps())) {
-            T d = (mn - r.o.y) / r.d.y;
-            if (check_cap(r, d, T(1))) ts[n++] = d;
-            d = (mx - r.o.y) / r.d.y;
-            if (check_cap(r, d, T(1))) ts[n++] = d;
+            T dlo, dhi;
+            cap_distances(mn - r.o.y, mx - r.o.y, r.d.y, dlo, dhi);
+            if (check_cap(r, dlo, T(1))) ts[n++] = dlo;
+            if (check_cap(r, dhi, T(1))) ts[n++] = dhi;
         }
     } else if (TYPE == 4) {  // shapes/cone.rs:81-112 + 41-59
         T mn = g[SHAPE_MIN], mx = g[SHAPE_MAX];
@@ -325,7 +382,7 @@ RT_DEV int local_intersect(const Ray<T>& r, const T* g, int flags, const T* tri,
         T c = sq(r.o.x) - sq(r.o.y) + sq(r.o.z);
         T d1, d2;
         if (fabs(a) < Real<T>::eps() && fabs(b) > Real<T>::eps()) {
-            ts[n++] = -c / (T(2) * b);
+            ts[n++] = div_exact(-c, T(2) * b);
         } else if (solve_quadratic(a, b, c, d1, d2)) {
             if (d1 > d2) {
                 T t = d1;
@@ -338,10 +395,10 @@ RT_DEV int local_intersect(const Ray<T>& r, const T* g, int flags, const T* tri,
             if (mn < y2 && y2 < mx) ts[n++] = d2;
         }
         if ((flags & FLAG_CLOSED) && !(fabs(r.d.y) < Real<T>::eps())) {
-            T d = (mn - r.o.y) / r.d.y;
-            if (check_cap(r, d, sq(mn))) ts[n++] = d;
-            d = (mx - r.o.y) / r.d.y;
-            if (check_cap(r, d, sq(mx))) ts[n++] = d;
+            T dlo, dhi;
+            cap_distances(mn - r.o.y, mx - r.o.y, r.d.y, dlo, dhi);
+            if (check_cap(r, dlo, sq(mn))) ts[n++] = dlo;
+            if (check_cap(r, dhi, sq(mx))) ts[n++] = dhi;
         }
     } else {  // shapes/triangle.rs:39-56
         V3<T> v1 = ld3(tri), e1 = ld3(tri + 3), e2 = ld3(tri + 6);
@@ -349,12 +406,25 @@ RT_DEV int local_intersect(const Ray<T>& r, const T* g, int flags, const T* tri,
         T det = dot(e1, dce2);
         if (!(fabs(det) < Real<T>::eps())) {
             V3<T> v1o = r.o - v1;
-            T u = dot(v1o, dce2) / det;
+            // u, v and the distance are three exact quotients by the same determinant
+            bool ok_r = true;
+            Recip<T> rd = recip(det, ok_r);
+            T un = dot(v1o, dce2);
+            bool ok_u = ok_r;
+            T u = quot(un, rd, ok_u);
+            if (!ok_u) u = un / det;
             if (u >= T(0) && u <= T(1)) {
                 V3<T> oce1 = cross(v1o, e1);
-                T v = dot(r.d, oce1) / det;
+                T vn = dot(r.d, oce1);
+                bool ok_v = ok_r;
+                T v = quot(vn, rd, ok_v);
+                if (!ok_v) v = vn / det;
                 if (v > T(0) && u + v < T(1)) {
-                    ts[0] = dot(e2, oce1) / det;
+                    T tn = dot(e2, oce1);
+                    bool ok_t = ok_r;
+                    T t = quot(tn, rd, ok_t);
+                    if (!ok_t) t = tn / det;
+                    ts[0] = t;
                     n = 1;
                 }
             }
@@ -749,9 +819,8 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
         if (state == ST_SHADOW && !after_lights) {
             // World::is_in_shadow, world.rs:98-112: next shadow ray
             V3<T> to_light = ld3(sv.light((uint32_t)light)) - over;
-            shadow_distance = magnitude(to_light);
             ray.o = over;
-            ray.d = normalized(to_light);
+            ray.d = normalized(to_light, &shadow_distance);  // magnitude() and normalized() take the same sqrt
             ++c_shadow;
         }
 

@@ -513,6 +513,31 @@ int measure_peak(int device, double* out_tflops, double* out_ms) {
     return RTGPU_OK;
 }
 
+__global__ void selftest_arith_kernel(const double* a, const double* b, size_t n, unsigned long long* out) {
+    unsigned long long div_bad = 0, sqrt_bad = 0, div_fb = 0, sqrt_fb = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double x = a[i], y = b[i];
+        bool ok = true;
+        rt::Recip<double> r = rt::recip(y, ok);
+        const double q = rt::quot(x, r, ok);
+        const double q_native = x / y;
+        if (!ok) ++div_fb;
+        else if (__double_as_longlong(q) != __double_as_longlong(q_native)) ++div_bad;
+        bool ok0 = true;
+        const double q0 = rt::quot0(x * 0.0, r, ok0);  // zero numerators keep the IEEE sign of zero
+        if (ok0 && __double_as_longlong(q0) != __double_as_longlong((x * 0.0) / y)) ++div_bad;
+        bool oks = true;
+        const double s = rt::sqrt_fast(x, oks);
+        const double s_native = sqrt(x);
+        if (!oks) ++sqrt_fb;
+        else if (__double_as_longlong(s) != __double_as_longlong(s_native)) ++sqrt_bad;
+    }
+    atomicAdd(&out[0], div_bad);
+    atomicAdd(&out[1], sqrt_bad);
+    atomicAdd(&out[2], div_fb);
+    atomicAdd(&out[3], sqrt_fb);
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -651,6 +676,33 @@ int rtgpu_measure_fma_peak(int device, uint32_t precision, double* out_tflops, d
     if (precision == RTGPU_PRECISION_F64) return measure_peak<double>(device, out_tflops, out_ms);
     if (precision == RTGPU_PRECISION_F32) return measure_peak<float>(device, out_tflops, out_ms);
     return fail(RTGPU_ERR_INVALID_ARGUMENT, "precision %u", precision);
+}
+
+int rtgpu_selftest_arith(int device, const double* a, const double* b, size_t n, uint64_t* out_div_mismatches,
+                         uint64_t* out_sqrt_mismatches, uint64_t* out_div_fallbacks, uint64_t* out_sqrt_fallbacks) {
+    if (!a || !b) return fail(RTGPU_ERR_INVALID_ARGUMENT, "operand array is NULL");
+    if (rtgpu_device_count() <= 0) return fail(RTGPU_ERR_NO_DEVICE, "no CUDA device available");
+    CUDA_TRY(cudaSetDevice(device));
+    double *da = nullptr, *db = nullptr;
+    unsigned long long* dout = nullptr;
+    CUDA_TRY(cudaMalloc(&da, std::max<size_t>(8, n * sizeof(double))));
+    CUDA_TRY(cudaMalloc(&db, std::max<size_t>(8, n * sizeof(double))));
+    CUDA_TRY(cudaMalloc(&dout, 4 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemcpy(da, a, n * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(db, b, n * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(dout, 0, 4 * sizeof(unsigned long long)));
+    selftest_arith_kernel<<<1184, 256>>>(da, db, n, dout);
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long h[4];
+    CUDA_TRY(cudaMemcpy(h, dout, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(da);
+    cudaFree(db);
+    cudaFree(dout);
+    if (out_div_mismatches) *out_div_mismatches = h[0];
+    if (out_sqrt_mismatches) *out_sqrt_mismatches = h[1];
+    if (out_div_fallbacks) *out_div_fallbacks = h[2];
+    if (out_sqrt_fallbacks) *out_sqrt_fallbacks = h[3];
+    return RTGPU_OK;
 }
 
 }  // extern "C"
