@@ -31,6 +31,10 @@
 
 namespace rt {
 
+#ifndef RT_CULL
+#define RT_CULL 1  // bounding-sphere pre-test in the intersection loop (exact results either way)
+#endif
+
 #ifndef RT_STRICT_SIGNED_ZERO
 // 1: keep the reference's `0.0 + ...` fold seeds and `+ m[r][3] * w` terms of Matrix*Point/Vector
 //    (matrix.rs:332-362) literally.  They can only change the SIGN of an exactly-zero component.
@@ -44,6 +48,7 @@ struct Real<double> {
     static __device__ __forceinline__ double eps() { return 0.00000008; }  // consts.rs:2
     static __device__ __forceinline__ double offset_eps() { return 0.00000008; }  // computed_hit.rs:33-34
     static __device__ __forceinline__ double max() { return DBL_MAX; }
+    static __device__ __forceinline__ double cull_shrink() { return 1.0 - 1.0e-9; }  // >> f64 rounding of the pre-test
 };
 template <>
 struct Real<float> {
@@ -51,6 +56,7 @@ struct Real<float> {
     // 8e-8 is below one f32 ulp at |x| >= 1: the fast mode needs its own offset.
     static __device__ __forceinline__ float offset_eps() { return 1.0e-3f; }
     static __device__ __forceinline__ float max() { return FLT_MAX; }
+    static __device__ __forceinline__ float cull_shrink() { return 1.0f - 1.0e-3f; }
 };
 
 template <typename T>
@@ -146,6 +152,7 @@ struct SceneView {
     RT_DEV const T* pattern(uint32_t p) const { return reals + L.pat_off + (size_t)p * PAT_REALS; }
     RT_DEV const int* pattern_meta(uint32_t p) const { return ints + L.pat_meta_off + p * PAT_INTS; }
     RT_DEV const T* light(uint32_t l) const { return reals + L.light_off + (size_t)l * LIGHT_REALS; }
+    RT_DEV const T* cull(uint32_t pos) const { return reals + L.cull_off + (size_t)pos * CULL_REALS; }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -176,6 +183,7 @@ struct ContainerAcc {
 template <typename T>
 struct TraceAcc {
     int mode;
+    T dir_sq;       // |direction|^2 of the ray being traced (refracted rays are not unit, world.rs:150)
     T best_t;       // RADIANCE: +max seed; SHADOW: light distance seed
     int best_orig;  // world order of the best hit (tie-break), INT_MAX seed
     int best_pos;   // sorted position of the best hit, -1 = none
@@ -442,6 +450,23 @@ template <typename T, int TYPE>
 RT_DEV void trace_type(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
     const uint32_t b = sv.L.type_begin[TYPE], e = sv.L.type_begin[TYPE + 1];
     for (uint32_t pos = b; pos < e; ++pos) {
+#if RT_CULL
+        if (TYPE != 1) {  // planes are unbounded
+            // Conservative pre-test against the shape's world-space bounding sphere (centre c, radius^2
+            // r2, inflated by the packer).  With oc = c - o and bq = oc.d, the ray's supporting line
+            // misses the sphere iff |oc|^2 |d|^2 - bq^2 > r2 |d|^2; if the origin is outside and the
+            // centre behind it (bq < 0) every intersection has a negative distance, which only the
+            // container walk cares about.  The shrink factor dwarfs the rounding of this test, and the
+            // inflation dwarfs the rounding of the exact test, so a culled shape yields no
+            // intersection in the reference's arithmetic either.
+            const T* cs = sv.cull(pos);
+            const T ocx = cs[0] - ray.o.x, ocy = cs[1] - ray.o.y, ocz = cs[2] - ray.o.z;
+            const T bq = fma(ocz, ray.d.z, fma(ocy, ray.d.y, ocx * ray.d.x));
+            const T c2 = fma(ocz, ocz, fma(ocy, ocy, ocx * ocx));
+            const T ex = fma(c2, Real<T>::cull_shrink(), -cs[3]);
+            if (ex > T(0) && ((acc.mode != MODE_CONTAINER && bq < T(0)) || ex * acc.dir_sq > bq * bq)) continue;
+        }
+#endif
         const T* g = sv.shape(pos);
         int4 meta = sv.shape_meta(pos);
         // ray.rs:45-49
@@ -670,6 +695,7 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
         TraceAcc<T> acc;
         acc.mode = (state == ST_RADIANCE) ? MODE_RADIANCE : (state == ST_SHADOW) ? MODE_SHADOW : (state == ST_CONTAINER) ? MODE_CONTAINER : MODE_IDLE;
         acc.best_t = (state == ST_SHADOW) ? shadow_distance : Real<T>::max();
+        acc.dir_sq = fma(ray.d.z, ray.d.z, fma(ray.d.y, ray.d.y, ray.d.x * ray.d.x));
         acc.best_orig = 0x7fffffff;
         acc.best_pos = -1;
         acc.c.t_hit = t_hit;

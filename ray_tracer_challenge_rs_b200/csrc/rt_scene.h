@@ -5,7 +5,7 @@
 // metadata, with the shapes grouped by type so that the intersection loops contain no dispatch:
 //
 //   real blob : [ shape geometry S x 16 ][ triangle data NT x 12 ][ materials M x 12 ]
-//               [ patterns Q x 18 ][ lights L x 6 ]
+//               [ patterns Q x 18 ][ lights L x 6 ][ cull spheres S x 4 ]
 //   int  blob : [ shape meta S x 4 ][ material meta M x 2 ][ pattern meta Q x 4 ]
 //
 // Both blobs are staged into shared memory by every CTA when they fit (always, for the shipped
@@ -58,6 +58,12 @@ constexpr int PAT_INTS = 4;
 // ---- light record: 6 reals: position[3], intensity[3] (primitives/light.rs:6-9) -----------------
 constexpr int LIGHT_REALS = 6;
 
+// ---- cull record: 4 reals: world-space bounding sphere centre[3], radius^2 (+inf = unbounded) ----
+// Not part of the reference: a conservative pre-test.  A ray whose supporting line stays outside the
+// (slightly inflated) sphere cannot produce an intersection in the reference's arithmetic either, so
+// skipping the exact test changes no result (rt_kernel.cuh, trace_type).
+constexpr int CULL_REALS = 4;
+
 constexpr int NUM_SHAPE_TYPES = 6;  // order = rtgpu_shape_type: sphere, plane, cube, cylinder, cone, triangle
 
 // What a kernel needs to find its way around the two blobs.  Passed by value as a kernel parameter.
@@ -65,7 +71,7 @@ struct SceneLayout {
     uint32_t n_shapes;
     uint32_t type_begin[NUM_SHAPE_TYPES + 1];  // sorted positions [type_begin[t], type_begin[t+1]) hold type t
     uint32_t n_materials, n_patterns, n_lights;
-    uint32_t tri_off, mat_off, pat_off, light_off;  // offsets into the real blob, in reals
+    uint32_t tri_off, mat_off, pat_off, light_off, cull_off;  // offsets into the real blob, in reals
     uint32_t mat_meta_off, pat_meta_off;            // offsets into the int blob, in int32
     uint32_t n_reals, n_ints;                       // blob sizes
     uint32_t in_shared;                             // 1: CTAs stage both blobs in shared memory

@@ -8,6 +8,8 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
+#include <limits>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -85,6 +87,125 @@ int validate_scene(const rtgpu_scene* s) {
     return RTGPU_OK;
 }
 
+// ---- conservative world-space bounding spheres (rt_scene.h CULL_REALS) ---------------------------
+
+// forward linear part M = A^-1 and translation p0 = -M t of the affine transform whose inverse is [A | t]
+bool invert_affine(const double* inv, double M[9], double p0[3]) {
+    const double a = inv[0], b = inv[1], c = inv[2], d = inv[4], e = inv[5], f = inv[6], g = inv[8], h = inv[9], k = inv[10];
+    const double det = a * (e * k - f * h) - b * (d * k - f * g) + c * (d * h - e * g);
+    if (!(std::fabs(det) > 0.0) || !std::isfinite(det)) return false;
+    const double id = 1.0 / det;
+    M[0] = (e * k - f * h) * id; M[1] = (c * h - b * k) * id; M[2] = (b * f - c * e) * id;
+    M[3] = (f * g - d * k) * id; M[4] = (a * k - c * g) * id; M[5] = (c * d - a * f) * id;
+    M[6] = (d * h - e * g) * id; M[7] = (b * g - a * h) * id; M[8] = (a * e - b * d) * id;
+    const double t[3] = {inv[3], inv[7], inv[11]};
+    for (int r = 0; r < 3; ++r) p0[r] = -(M[r * 3 + 0] * t[0] + M[r * 3 + 1] * t[1] + M[r * 3 + 2] * t[2]);
+    for (int i = 0; i < 9; ++i)
+        if (!std::isfinite(M[i])) return false;
+    return std::isfinite(p0[0]) && std::isfinite(p0[1]) && std::isfinite(p0[2]);
+}
+
+void mat3_apply(const double M[9], const double v[3], double out[3]) {
+    for (int r = 0; r < 3; ++r) out[r] = M[r * 3 + 0] * v[0] + M[r * 3 + 1] * v[1] + M[r * 3 + 2] * v[2];
+}
+
+// largest singular value of M (cyclic Jacobi on M^T M), rounded up
+double sigma_max(const double M[9]) {
+    double S[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) S[i][j] = M[0 * 3 + i] * M[0 * 3 + j] + M[1 * 3 + i] * M[1 * 3 + j] + M[2 * 3 + i] * M[2 * 3 + j];
+    for (int sweep = 0; sweep < 32; ++sweep) {
+        const double off = std::fabs(S[0][1]) + std::fabs(S[0][2]) + std::fabs(S[1][2]);
+        if (off <= 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (S[p][q] == 0.0) continue;
+                const double theta = (S[q][q] - S[p][p]) / (2.0 * S[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+                for (int r = 0; r < 3; ++r) {  // S = S * J
+                    const double srp = S[r][p], srq = S[r][q];
+                    S[r][p] = c * srp - sn * srq;
+                    S[r][q] = sn * srp + c * srq;
+                }
+                for (int r = 0; r < 3; ++r) {  // S = J^T * S
+                    const double spr = S[p][r], sqr = S[q][r];
+                    S[p][r] = c * spr - sn * sqr;
+                    S[q][r] = sn * spr + c * sqr;
+                }
+            }
+    }
+    const double lam = std::max(S[0][0], std::max(S[1][1], S[2][2]));
+    // Gershgorin slack for whatever off-diagonal mass is left, then a relative safety factor
+    const double slack = std::fabs(S[0][1]) + std::fabs(S[0][2]) + std::fabs(S[1][2]);
+    return std::sqrt(std::max(0.0, lam + slack)) * (1.0 + 1e-9);
+}
+
+void bounding_sphere(const rtgpu_scene* s, uint32_t i, double out[4]) {
+    const double inf = std::numeric_limits<double>::infinity();
+    out[0] = out[1] = out[2] = 0.0;
+    out[3] = inf;  // unbounded: never culled
+    const int type = s->shape_type[i];
+    if (type == RTGPU_PLANE) return;
+    double M[9], p0[3];
+    if (!invert_affine(s->shape_inv + (size_t)i * 12, M, p0)) return;
+    double centre_local[3] = {0, 0, 0};
+    double radius = inf;
+    if (type == RTGPU_SPHERE) {
+        radius = sigma_max(M);
+    } else if (type == RTGPU_CUBE) {
+        radius = 0.0;
+        for (int c = 0; c < 8; ++c) {
+            const double v[3] = {(c & 1) ? 1.0 : -1.0, (c & 2) ? 1.0 : -1.0, (c & 4) ? 1.0 : -1.0};
+            double w[3];
+            mat3_apply(M, v, w);
+            radius = std::max(radius, std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]));
+        }
+    } else if (type == RTGPU_CYLINDER || type == RTGPU_CONE) {
+        const double mn = s->shape_min[i], mx = s->shape_max[i];
+        if (!(std::isfinite(mn) && std::isfinite(mx)) || std::fabs(mn) > 1e150 || std::fabs(mx) > 1e150 || !(mn <= mx)) return;
+        const double ym = 0.5 * (mn + mx);
+        centre_local[1] = ym;
+        double local_r;
+        if (type == RTGPU_CYLINDER) {
+            const double hgt = 0.5 * (mx - mn);
+            local_r = std::sqrt(1.0 + hgt * hgt);
+        } else {
+            // cone surface: radius |y| at height y; caps included
+            const double r_lo = std::sqrt(mn * mn + (mn - ym) * (mn - ym)), r_hi = std::sqrt(mx * mx + (mx - ym) * (mx - ym));
+            local_r = std::max(r_lo, r_hi);
+        }
+        radius = sigma_max(M) * local_r;
+    } else if (type == RTGPU_TRIANGLE) {
+        const size_t t = (size_t)s->shape_triangle[i] * 3;
+        double v[3][3];
+        for (int k = 0; k < 3; ++k) {
+            v[0][k] = s->tri_vertex_1[t + k];
+            v[1][k] = s->tri_vertex_1[t + k] + s->tri_edge_1[t + k];
+            v[2][k] = s->tri_vertex_1[t + k] + s->tri_edge_2[t + k];
+            centre_local[k] = (v[0][k] + v[1][k] + v[2][k]) / 3.0;
+        }
+        radius = 0.0;
+        for (int j = 0; j < 3; ++j) {
+            const double dl[3] = {v[j][0] - centre_local[0], v[j][1] - centre_local[1], v[j][2] - centre_local[2]};
+            double w[3];
+            mat3_apply(M, dl, w);
+            radius = std::max(radius, std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]));
+        }
+    }
+    double cw[3];
+    mat3_apply(M, centre_local, cw);
+    const double cx = p0[0] + cw[0], cy = p0[1] + cw[1], cz = p0[2] + cw[2];
+    // inflate: relative 1e-6 plus an absolute term for the rounding of the centre itself
+    const double scale = std::fabs(cx) + std::fabs(cy) + std::fabs(cz) + radius;
+    const double r = radius * (1.0 + 1e-6) + scale * 1e-12;
+    if (!(std::isfinite(r) && std::isfinite(cx) && std::isfinite(cy) && std::isfinite(cz)) || r * r > 1e300) return;
+    out[0] = cx;
+    out[1] = cy;
+    out[2] = cz;
+    out[3] = r * r;
+}
+
 int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     int st = validate_scene(s);
     if (st != RTGPU_OK) return st;
@@ -119,7 +240,8 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     lay.mat_off = lay.tri_off + n_tri * rt::TRI_REALS;
     lay.pat_off = lay.mat_off + M * rt::MAT_REALS;
     lay.light_off = lay.pat_off + Q * rt::PAT_REALS;
-    lay.n_reals = lay.light_off + L * rt::LIGHT_REALS;
+    lay.cull_off = (lay.light_off + L * rt::LIGHT_REALS + 1u) & ~1u;  // 16-byte aligned records
+    lay.n_reals = lay.cull_off + S * rt::CULL_REALS;
     lay.n_reals = (lay.n_reals + 1u) & ~1u;
     lay.mat_meta_off = S * rt::SHAPE_INTS;
     lay.pat_meta_off = lay.mat_meta_off + M * rt::MAT_INTS;
@@ -148,6 +270,7 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
         m[1] = (int)mat;
         m[2] = flags;
         m[3] = (int)cls;
+        bounding_sphere(s, i, R + lay.cull_off + (size_t)pos * rt::CULL_REALS);
         if (s->shape_type[i] == RTGPU_TRIANGLE) {
             const size_t t = (size_t)s->shape_triangle[i] * 3;
             double* td = R + lay.tri_off + (size_t)(pos - lay.type_begin[5]) * rt::TRI_REALS;
@@ -524,7 +647,8 @@ __global__ void selftest_arith_kernel(const double* a, const double* b, size_t n
         if (!ok) ++div_fb;
         else if (__double_as_longlong(q) != __double_as_longlong(q_native)) ++div_bad;
         bool ok0 = true;
-        const double q0 = rt::quot0(x * 0.0, r, ok0);  // zero numerators keep the IEEE sign of zero
+        rt::Recip<double> r0 = rt::recip(y, ok0);
+        const double q0 = rt::quot0(x * 0.0, r0, ok0);  // zero numerators keep the IEEE sign of zero
         if (ok0 && __double_as_longlong(q0) != __double_as_longlong((x * 0.0) / y)) ++div_bad;
         bool oks = true;
         const double s = rt::sqrt_fast(x, oks);
