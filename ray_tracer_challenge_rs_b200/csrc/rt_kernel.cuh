@@ -69,6 +69,17 @@ struct Ray {
 };
 
 #define RT_DEV __device__ __forceinline__
+// Rarely executed or multiply used helpers are kept out of line: the kernel's hot working set must
+// stay inside the 32 KB L1.5 instruction cache (the first culled build spent 44 % of its stall
+// samples on instruction fetch, profiles/r1_notes.md).
+#ifndef RT_OUTLINE
+#define RT_OUTLINE 1
+#endif
+#if RT_OUTLINE
+#define RT_COLD __device__ __noinline__
+#else
+#define RT_COLD __device__ __forceinline__
+#endif
 
 template <typename T> RT_DEV V3<T> mk(T x, T y, T z) { V3<T> r; r.x = x; r.y = y; r.z = z; return r; }
 template <typename T> RT_DEV V3<T> ld3(const T* p) { return mk<T>(p[0], p[1], p[2]); }
@@ -85,21 +96,32 @@ template <typename T> RT_DEV T dot(V3<T> a, V3<T> b) { return fma(a.z, b.z, fma(
 template <typename T> RT_DEV V3<T> cross(V3<T> a, V3<T> b) {
     return mk<T>(fma(a.y, b.z, -a.z * b.y), fma(a.z, b.x, -a.x * b.z), fma(a.x, b.y, -a.y * b.x));
 }
+template <typename T> RT_COLD T div_native(T a, T b) { return a / b; }
+template <typename T> RT_COLD T sqrt_native(T a) { return sqrt(a); }
+
 // vector.rs:84-91: magnitude = sqrt(x^2 + y^2 + z^2); normalized DIVIDES each component by it.
 // One exact sqrt + one shared reciprocal for the three exact quotients (rt_arith.cuh).
-template <typename T> RT_DEV V3<T> normalized(V3<T> a, T* magnitude_out = nullptr) {
+template <typename T>
+struct Normalized {
+    V3<T> v;
+    T magnitude;
+};
+template <typename T> RT_COLD Normalized<T> normalize_full(V3<T> a) {
     bool ok = true;
     T s = sq(a.x) + sq(a.y) + sq(a.z);
     T m = sqrt_fast(s, ok);
     Recip<T> r = recip(m, ok);
     V3<T> q = mk<T>(quot0(a.x, r, ok), quot0(a.y, r, ok), quot0(a.z, r, ok));
     if (!ok) {
-        m = sqrt(s);
-        q = mk<T>(a.x / m, a.y / m, a.z / m);
+        m = sqrt_native(s);
+        q = mk<T>(div_native(a.x, m), div_native(a.y, m), div_native(a.z, m));
     }
-    if (magnitude_out) *magnitude_out = m;
-    return q;
+    Normalized<T> out;
+    out.v = q;
+    out.magnitude = m;
+    return out;
 }
+template <typename T> RT_DEV V3<T> normalized(V3<T> a) { return normalize_full(a).v; }
 // vector.rs:105-107
 template <typename T> RT_DEV V3<T> reflect(V3<T> v, V3<T> n) { return v - ((n * T(2)) * dot(v, n)); }
 
@@ -251,16 +273,16 @@ RT_DEV bool solve_quadratic(T a, T b, T c, T& s1, T& s2) {
     s1 = quot(-b - root, r, ok);
     s2 = quot(-b + root, r, ok);
     if (!ok) {
-        root = sqrt(discriminant);
-        s1 = (-b - root) / double_a;
-        s2 = (-b + root) / double_a;
+        root = sqrt_native(discriminant);
+        s1 = div_native(-b - root, double_a);
+        s2 = div_native(-b + root, double_a);
     }
     return true;
 }
 
 // shapes/cube.rs:22-43, native operators (fallback of cube_axis_fast)
 template <typename T>
-RT_DEV void cube_check_axis(T origin, T direction, T& tmin, T& tmax) {
+RT_COLD void cube_check_axis(T origin, T direction, T& tmin, T& tmax) {
     T nmin = T(-1) - origin;
     T nmax = T(1) - origin;
     T dmin, dmax;
@@ -315,8 +337,8 @@ RT_DEV void cap_distances(T nlo, T nhi, T dy, T& dlo, T& dhi) {
     dlo = quot(nlo, r, ok);
     dhi = quot(nhi, r, ok);
     if (!ok) {
-        dlo = nlo / dy;
-        dhi = nhi / dy;
+        dlo = div_native(nlo, dy);
+        dhi = div_native(nhi, dy);
     }
 }
 
@@ -420,18 +442,18 @@ RT_DEV int local_intersect(const Ray<T>& r, const T* g, int flags, const T* tri,
             T un = dot(v1o, dce2);
             bool ok_u = ok_r;
             T u = quot(un, rd, ok_u);
-            if (!ok_u) u = un / det;
+            if (!ok_u) u = div_native(un, det);
             if (u >= T(0) && u <= T(1)) {
                 V3<T> oce1 = cross(v1o, e1);
                 T vn = dot(r.d, oce1);
                 bool ok_v = ok_r;
                 T v = quot(vn, rd, ok_v);
-                if (!ok_v) v = vn / det;
+                if (!ok_v) v = div_native(vn, det);
                 if (v > T(0) && u + v < T(1)) {
                     T tn = dot(e2, oce1);
                     bool ok_t = ok_r;
                     T t = quot(tn, rd, ok_t);
-                    if (!ok_t) t = tn / det;
+                    if (!ok_t) t = div_native(tn, det);
                     ts[0] = t;
                     n = 1;
                 }
@@ -479,14 +501,18 @@ RT_DEV void trace_type(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& a
     }
 }
 
-template <typename T>
+// FULL = false: the scene holds only spheres, planes and cubes (all but one shipped scene); the
+// cylinder / cone / triangle loops are not even instantiated, which keeps the code footprint down.
+template <typename T, bool FULL>
 RT_DEV void trace(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
     trace_type<T, 0>(sv, ray, acc);
     trace_type<T, 1>(sv, ray, acc);
     trace_type<T, 2>(sv, ray, acc);
-    trace_type<T, 3>(sv, ray, acc);
-    trace_type<T, 4>(sv, ray, acc);
-    trace_type<T, 5>(sv, ray, acc);
+    if (FULL) {
+        trace_type<T, 3>(sv, ray, acc);
+        trace_type<T, 4>(sv, ray, acc);
+        trace_type<T, 5>(sv, ray, acc);
+    }
 }
 
 RT_DEV int shape_type_of(const SceneLayout& L, uint32_t pos) {
@@ -502,7 +528,7 @@ template <typename T> RT_DEV bool coarse_eq(T a, T b) { return a == b || fabs(a 
 // local_normal_at of the six shapes (sphere.rs:57-59, plane.rs:52-54, cube.rs:89-101,
 // cylinder.rs:114-126, cone.rs:116-133, triangle.rs:78-80)
 template <typename T>
-RT_DEV V3<T> local_normal_at(const SceneView<T>& sv, uint32_t pos, int type, const T* g, V3<T> p) {
+RT_COLD V3<T> local_normal_at(const SceneView<T>& sv, uint32_t pos, int type, const T* g, V3<T> p) {
     switch (type) {
     case 0: return p;
     case 1: return mk<T>(T(0), T(1), T(0));
@@ -542,7 +568,7 @@ RT_DEV bool even_as_i64(T v) {
 
 // Pattern::color_at (patterns/*.rs) at pattern-space point p
 template <typename T>
-RT_DEV V3<T> pattern_color_at(const SceneView<T>& sv, int pattern, V3<T> p) {
+RT_COLD V3<T> pattern_color_at(const SceneView<T>& sv, int pattern, V3<T> p) {
     for (;;) {
         const T* pr = sv.pattern(pattern);
         const int* pm = sv.pattern_meta(pattern);
@@ -585,10 +611,14 @@ enum : int { ST_FETCH = 0, ST_RADIANCE = 1, ST_CONTAINER = 2, ST_SHADOW = 3, ST_
 #define RT_MIN_BLOCKS_PER_SM 3
 #endif
 
+#ifndef RT_TILE_ORDER
+#define RT_TILE_ORDER 0
+#endif
+
 constexpr int TILE_W = 8, TILE_H = 4;   // a warp's 32 pixel slots = one 8x4 tile
 constexpr int CHUNK_SLOTS = 64;         // slots a warp takes from the global counter at a time
 
-template <typename T, int MAX_FRAMES>
+template <typename T, int MAX_FRAMES, bool FULL>
 __global__ void __launch_bounds__(RT_BLOCK_THREADS, RT_MIN_BLOCKS_PER_SM)
 render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, SceneLayout layout, CameraParams<T> cam,
               T* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8, unsigned long long* __restrict__ counters,
@@ -661,8 +691,18 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
                     state = ST_DONE;  // unless the slot is a real pixel
                     if (slot < total_slots) {
                         uint32_t tile = slot / (TILE_W * TILE_H), in = slot % (TILE_W * TILE_H);
+                        uint32_t tile_row = tile / tiles_x;
+#if RT_TILE_ORDER == 1
+                        // rows of tiles from the middle of the frame outwards: the expensive pixels of a
+                        // typical scene (glass, mirrors) sit near the centre and should start first
+                        {
+                            const uint32_t mid = tiles_y / 2;
+                            const uint32_t h = (tile_row + 1) / 2;
+                            tile_row = (tile_row & 1u) ? (mid >= h ? mid - h : tiles_y - 1 - (h - mid - 1)) : (mid + h < tiles_y ? mid + h : (tiles_y - 1) - (mid + h - tiles_y));
+                        }
+#endif
                         uint32_t x = (tile % tiles_x) * TILE_W + in % TILE_W;
-                        uint32_t k = (tile / tiles_x) * TILE_H + in / TILE_W;
+                        uint32_t k = tile_row * TILE_H + in / TILE_W;
                         state = ST_FETCH;  // padding slot: try again on the next round
                         if (x < cam.hsize && k < cam.n_rows) {
                             uint32_t y = ((k / cam.band_rows) * cam.shard_count + cam.shard_index) * cam.band_rows + k % cam.band_rows;
@@ -704,7 +744,7 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
         acc.c.all_pos = acc.c.excl_pos = -1;
         acc.c.all_t = acc.c.excl_t = T(0);
         acc.c.all_orig = acc.c.excl_orig = 0;
-        if (acc.mode != MODE_IDLE) trace(sv, ray, acc);
+        if (acc.mode != MODE_IDLE) trace<T, FULL>(sv, ray, acc);
 
         // ---- phase C: consume the result ------------------------------------------------------------
         bool finish_hit = false;     // ComputedHit complete -> start the light loop
@@ -846,7 +886,9 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
             // World::is_in_shadow, world.rs:98-112: next shadow ray
             V3<T> to_light = ld3(sv.light((uint32_t)light)) - over;
             ray.o = over;
-            ray.d = normalized(to_light, &shadow_distance);  // magnitude() and normalized() take the same sqrt
+            Normalized<T> nl = normalize_full(to_light);  // magnitude() and normalized() take the same sqrt
+            ray.d = nl.v;
+            shadow_distance = nl.magnitude;
             ++c_shadow;
         }
 

@@ -360,10 +360,10 @@ struct rtgpu_context {
 
 namespace {
 
-template <typename T, int MAX_FRAMES>
-int launch_kernel(rtgpu_context* ctx, const T* d_reals, const rt::CameraParams<T>& cam, T* d_out, uint8_t* d_out8,
-                  unsigned long long* d_counters, cudaStream_t stream) {
-    auto kernel = rt::render_kernel<T, MAX_FRAMES>;
+template <typename T, int MAX_FRAMES, bool FULL>
+int launch_kernel_impl(rtgpu_context* ctx, const T* d_reals, const rt::CameraParams<T>& cam, T* d_out, uint8_t* d_out8,
+                       unsigned long long* d_counters, cudaStream_t stream) {
+    auto kernel = rt::render_kernel<T, MAX_FRAMES, FULL>;
     rt::SceneLayout lay = ctx->layout;
     size_t smem = (((size_t)lay.n_reals * sizeof(T) + 15) & ~size_t(15)) + (size_t)lay.n_ints * sizeof(int);
     // keep at least ~3 CTAs of 128 threads per SM resident: stage in shared memory only when small enough
@@ -385,6 +385,15 @@ int launch_kernel(rtgpu_context* ctx, const T* d_reals, const rt::CameraParams<T
     kernel<<<(unsigned)grid, RT_BLOCK_THREADS, smem, stream>>>(d_reals, ctx->d_ints, lay, cam, d_out, d_out8, d_counters, ctx->d_work);
     CUDA_TRY(cudaGetLastError());
     return RTGPU_OK;
+}
+
+template <typename T, int MAX_FRAMES>
+int launch_kernel(rtgpu_context* ctx, const T* d_reals, const rt::CameraParams<T>& cam, T* d_out, uint8_t* d_out8,
+                  unsigned long long* d_counters, cudaStream_t stream) {
+    // scenes without cylinders, cones and triangles run the kernel instantiated without those loops
+    const bool full = ctx->layout.type_begin[3] != ctx->layout.type_begin[6];
+    if (full) return launch_kernel_impl<T, MAX_FRAMES, true>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    return launch_kernel_impl<T, MAX_FRAMES, false>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
 }
 
 template <typename T>
