@@ -37,8 +37,12 @@ namespace rt {
 
 #ifndef RT_STRICT_SIGNED_ZERO
 // 1: keep the reference's `0.0 + ...` fold seeds and `+ m[r][3] * w` terms of Matrix*Point/Vector
-//    (matrix.rs:332-362) literally.  They can only change the SIGN of an exactly-zero component.
-#define RT_STRICT_SIGNED_ZERO 1
+//    (matrix.rs:332-362) literally.  `0.0 + p` differs from `p` only for p = -0.0, and `x + m*0.0`
+//    differs from `x` only for x = -0.0, so the terms can only turn a -0.0 component into +0.0.
+//    Nothing on the path can tell the two zeros apart (every division is guarded by an EPSILON or
+//    `> 0.0` test, comparisons treat them as equal, `floor(-0.0) as i64` = 0): the default build
+//    drops the 12 extra FP64 operations per ray-shape test.  DESIGN.md, "signed zeros".
+#define RT_STRICT_SIGNED_ZERO 0
 #endif
 
 template <typename T>
@@ -608,11 +612,15 @@ enum : int { ST_FETCH = 0, ST_RADIANCE = 1, ST_CONTAINER = 2, ST_SHADOW = 3, ST_
 #define RT_BLOCK_THREADS 128
 #endif
 #ifndef RT_MIN_BLOCKS_PER_SM
-#define RT_MIN_BLOCKS_PER_SM 3
+#define RT_MIN_BLOCKS_PER_SM 4
 #endif
 
 #ifndef RT_TILE_ORDER
-#define RT_TILE_ORDER 0
+// 0 scanline, 1 middle-out, 2 bottom-up, 3 scattered.  Per-pixel cost varies by 50x and is spatially
+// clustered; in scanline order the expensive rows of a typical frame (floor reflections, glass) come
+// last and the launch ends with a long thin tail (measured: 5.17 ms scanline vs 4.39 ms heavy-first
+// vs 4.53 ms scattered on cover@1080p).  Scattered needs no knowledge of the scene.
+#define RT_TILE_ORDER 3
 #endif
 
 constexpr int TILE_W = 8, TILE_H = 4;   // a warp's 32 pixel slots = one 8x4 tile
@@ -699,6 +707,16 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
                             const uint32_t mid = tiles_y / 2;
                             const uint32_t h = (tile_row + 1) / 2;
                             tile_row = (tile_row & 1u) ? (mid >= h ? mid - h : tiles_y - 1 - (h - mid - 1)) : (mid + h < tiles_y ? mid + h : (tiles_y - 1) - (mid + h - tiles_y));
+                        }
+#elif RT_TILE_ORDER == 2
+                        tile_row = tiles_y - 1 - tile_row;  // bottom-up (experiment)
+#elif RT_TILE_ORDER == 3
+                        // scattered: a multiplicative permutation of the tile index (stride coprime to the
+                        // tile count), so that every part of the frame is sampled all along the launch
+                        {
+                            const uint32_t n_tiles = tiles_x * tiles_y;
+                            tile = (uint32_t)(((unsigned long long)tile * cam.tile_stride) % n_tiles);
+                            tile_row = tile / tiles_x;
                         }
 #endif
                         uint32_t x = (tile % tiles_x) * TILE_W + in % TILE_W;

@@ -88,6 +88,7 @@ struct CameraParams {
     uint32_t n_rows;  // rows rendered by this launch
     uint32_t band_rows, shard_index, shard_count;
     uint32_t max_depth;  // World::MAX_REFLECTION_ITERATIONS (world.rs:15)
+    uint32_t tile_stride;  // coprime to the number of 8x4 tiles: scattered tile order (rt_kernel.cuh)
 };
 
 // Work counters, in the order of the first six fields of rtgpu_stats.

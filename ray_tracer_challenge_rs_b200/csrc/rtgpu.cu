@@ -410,6 +410,14 @@ void fill_camera(const rtgpu_camera* c, const RowSel& rows, uint32_t n_rows, uin
     out->shard_index = rows.shard_index;
     out->shard_count = rows.shard_count;
     out->max_depth = max_depth;
+    // stride for the scattered tile order: near the golden ratio of the tile count, made coprime to it
+    const uint64_t n_tiles = (uint64_t)((c->hsize + rt::TILE_W - 1) / rt::TILE_W) * ((n_rows + rt::TILE_H - 1) / rt::TILE_H);
+    uint64_t stride = (uint64_t)((double)n_tiles * 0.6180339887498949);
+    if (stride < 1) stride = 1;
+    auto gcd = [](uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; };
+    while (n_tiles > 1 && gcd(stride, n_tiles) != 1) ++stride;
+    out->tile_stride = (uint32_t)(n_tiles > 1 ? stride % n_tiles : 0);
+    if (n_tiles > 1 && out->tile_stride == 0) out->tile_stride = 1;
 }
 
 int ensure_f32_blob(rtgpu_context* ctx, cudaStream_t stream) {
