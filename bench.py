@@ -210,9 +210,18 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    host_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # CPU-side barrier for the leg where rank 0 alone drives every device: an NCCL barrier would park
+        # a spinning kernel on the other ranks' GPUs and steal SM time from the frame being measured
+        host_group = dist.new_group(backend="gloo")
+
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=host_group)
 
     def barrier():
         if world > 1:
@@ -285,7 +294,8 @@ def run_b200(args):
         from ray_tracer_challenge_rs_b200.flatten import camera_to_c
 
         cscene, ccam = flat.as_c(), camera_to_c(camera)
-        opts = abi.RtgpuOpts(abi.PRECISION_F64 if args.precision == "f64" else abi.PRECISION_F32, args.max_depth, world, 16, 0)
+        e2e_gpus = max(1, min(world, lib.rtgpu_device_count()))
+        opts = abi.RtgpuOpts(abi.PRECISION_F64 if args.precision == "f64" else abi.PRECISION_F32, args.max_depth, e2e_gpus, 16, 0)
         st = abi.RtgpuStats()
 
         def one_frame():
@@ -293,7 +303,7 @@ def run_b200(args):
 
     if world > 1:
         renderer.close()  # rank 0's one-shot call owns every device for the e2e leg
-    barrier()
+    host_barrier()
     if rank == 0:
         for _ in range(W):
             one_frame()
@@ -305,11 +315,12 @@ def run_b200(args):
         scene_bytes = int(flat.n_shapes * 16 * 8 + flat.n_triangles * 12 * 8 + flat.n_materials * 12 * 8 + flat.n_patterns * 18 * 8 +
                           flat.n_lights * 6 * 8 + flat.n_shapes * 16 + flat.n_materials * 8 + flat.n_patterns * 16)
         e2e = {"value": st.as_dict()["rays"] / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": e2e_ms,
-               "h2d_bytes_per_step": scene_bytes * world + 256 * world, "d2h_bytes_per_step": n_px * 3 * elem + 48 * world,
+               "h2d_bytes_per_step": scene_bytes * e2e_gpus + 256 * e2e_gpus, "d2h_bytes_per_step": n_px * 3 * elem + 48 * e2e_gpus,
+               "n_gpus": e2e_gpus,
                "call": "rtgpu_render (scene pack + upload, kernel on N devices in 16-row bands, D2H of the full f64 Canvas into pinned host memory)",
                "kernel_ms_max_over_devices": st.kernel_ms}
         assert st.as_dict()["rays"] == rays, (st.as_dict(), stats)
-    barrier()
+    host_barrier()
 
     if rank == 0:
         # ---- roofline of the render kernel: FP-pipe ----
