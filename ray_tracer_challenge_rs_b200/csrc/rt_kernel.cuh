@@ -24,6 +24,7 @@
 #pragma once
 
 #include <cfloat>
+#include <climits>
 #include <cstdint>
 
 #include "rt_arith.cuh"
@@ -171,8 +172,10 @@ struct SceneView {
     const int* ints;
     SceneLayout L;
     RT_DEV const T* shape(uint32_t pos) const { return reals + (size_t)pos * SHAPE_REALS; }
-    RT_DEV int4 shape_meta(uint32_t pos) const { return reinterpret_cast<const int4*>(ints)[pos]; }
-    RT_DEV const T* triangle(uint32_t pos) const { return reals + L.tri_off + (size_t)(pos - L.type_begin[5]) * TRI_REALS; }
+    RT_DEV int4 shape_meta(uint32_t pos) const { return reinterpret_cast<const int4*>(ints)[(size_t)pos * (SHAPE_INTS / 4)]; }
+    RT_DEV const T* triangle(uint32_t pos) const { return reals + L.tri_off + (size_t)ints[(size_t)pos * SHAPE_INTS + 4] * TRI_REALS; }
+    RT_DEV const T* bvh_boxes(uint32_t node) const { return reals + L.bvh_off + (size_t)node * BVH_REALS; }
+    RT_DEV int2 bvh_children(uint32_t node) const { return reinterpret_cast<const int2*>(ints + L.bvh_meta_off)[node]; }
     RT_DEV const T* material(uint32_t m) const { return reals + L.mat_off + (size_t)m * MAT_REALS; }
     RT_DEV int material_pattern(uint32_t m) const { return ints[L.mat_meta_off + m * MAT_INTS]; }
     RT_DEV const T* pattern(uint32_t p) const { return reals + L.pat_off + (size_t)p * PAT_REALS; }
@@ -471,7 +474,21 @@ RT_DEV int local_intersect(const Ray<T>& r, const T* g, int flags, const T* tri,
     return n;
 }
 
-// World::collect_intersections (world.rs:25-35) for one shape type: every shape, no dispatch.
+// Ray::intersect (ray.rs:35-49) for the shape at sorted position `pos`, of (compile-time) type TYPE:
+// object-space ray, local_intersect, then the query's bookkeeping.
+template <typename T, int TYPE>
+RT_DEV void test_shape(const SceneView<T>& sv, uint32_t pos, const Ray<T>& ray, TraceAcc<T>& acc) {
+    const T* g = sv.shape(pos);
+    int4 meta = sv.shape_meta(pos);
+    Ray<T> local;
+    local.o = mat_point(g, ray.o);
+    local.d = mat_vector(g, ray.d);
+    T t0, t1, t2, t3;
+    int n = local_intersect<T, TYPE>(local, g, meta.z, TYPE == 5 ? sv.triangle(pos) : nullptr, t0, t1, t2, t3);
+    consume(acc, n, t0, t1, t2, t3, (int)pos, meta);
+}
+
+// World::collect_intersections (world.rs:25-35) over the flat per-type lists: every shape, no dispatch.
 template <typename T, int TYPE>
 RT_DEV void trace_type(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
     const uint32_t b = sv.L.type_begin[TYPE], e = sv.L.type_begin[TYPE + 1];
@@ -493,15 +510,94 @@ RT_DEV void trace_type(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& a
             if (ex > T(0) && ((acc.mode != MODE_CONTAINER && bq < T(0)) || ex * acc.dir_sq > bq * bq)) continue;
         }
 #endif
-        const T* g = sv.shape(pos);
-        int4 meta = sv.shape_meta(pos);
-        // ray.rs:45-49
-        Ray<T> local;
-        local.o = mat_point(g, ray.o);
-        local.d = mat_vector(g, ray.d);
-        T t0, t1, t2, t3;
-        int n = local_intersect<T, TYPE>(local, g, meta.z, TYPE == 5 ? sv.triangle(pos) : nullptr, t0, t1, t2, t3);
-        consume(acc, n, t0, t1, t2, t3, (int)pos, meta);
+        test_shape<T, TYPE>(sv, pos, ray, acc);
+    }
+}
+
+// ---- BVH traversal (scenes with many bounded shapes; rt_bvh.h) -----------------------------------
+// Each lane walks the hierarchy with its own small stack.  A child is entered iff the ray's parameter
+// interval inside its (inflated) box meets the interval the query still cares about:
+//   RADIANCE  [0, best_t]   (shrinks as hits are found; `<=` keeps equal-distance candidates, which the
+//                            world-order tie-break may still prefer)
+//   SHADOW    [0, best_t]   with best_t = light distance; the walk stops at the first blocker
+//   CONTAINER (-inf, t_hit] (every intersection before the hit, negative distances included)
+// Exact tests of the leaves are batched by shape type across the warp: the lanes that currently hold
+// a leaf of the elected type run that type's test together, so a warp never executes two shape types'
+// code at once.
+template <typename T>
+RT_DEV bool box_hit(const T* b, const Ray<T>& ray, V3<T> inv, T t_lo, T t_hi, T& enter) {
+    // slab test; fmin/fmax drop the NaN of 0 * inf (ray parallel to a slab and exactly on its face)
+    T x1 = (b[0] - ray.o.x) * inv.x, x2 = (b[3] - ray.o.x) * inv.x;
+    T y1 = (b[1] - ray.o.y) * inv.y, y2 = (b[4] - ray.o.y) * inv.y;
+    T z1 = (b[2] - ray.o.z) * inv.z, z2 = (b[5] - ray.o.z) * inv.z;
+    T tn = fmax(fmax(fmin(x1, x2), fmin(y1, y2)), fmax(fmin(z1, z2), t_lo));
+    T tf = fmin(fmin(fmax(x1, x2), fmax(y1, y2)), fmin(fmax(z1, z2), t_hi));
+    enter = tn;
+    return tn <= tf;
+}
+
+template <typename T, bool FULL>
+RT_DEV void trace_bvh(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
+    const bool active = acc.mode != MODE_IDLE;
+    // 1 / d per axis; only used for the conservative box tests, so plain reciprocals are enough.
+    // A zero component gives +-inf, which the slab test handles.
+    V3<T> inv = mk<T>(T(1) / ray.d.x, T(1) / ray.d.y, T(1) / ray.d.z);
+    const T t_lo = (acc.mode == MODE_CONTAINER) ? -Real<T>::max() : T(0);
+    int stack[BVH_MAX_DEPTH + 4];
+    int sp = 0;
+    int cur = active ? 0 : INT_MIN;  // INT_MIN = nothing left to visit; >= 0 inner node; < 0 leaf ~pos
+    int pending = -1;                // leaf waiting for its exact test
+    for (;;) {
+        while (pending < 0 && cur != INT_MIN) {
+            if (cur < 0) {
+                pending = ~cur;
+                cur = sp > 0 ? stack[--sp] : INT_MIN;
+                break;
+            }
+            const T* nb = sv.bvh_boxes((uint32_t)cur);
+            const int2 ch = sv.bvh_children((uint32_t)cur);
+            const T t_hi = (acc.mode == MODE_CONTAINER) ? acc.c.t_hit : acc.best_t;
+            T e0, e1;
+            const bool h0 = box_hit(nb, ray, inv, t_lo, t_hi, e0);
+            const bool h1 = box_hit(nb + 6, ray, inv, t_lo, t_hi, e1);
+            if (h0 && h1) {
+                const bool near0 = e0 <= e1;
+                stack[sp++] = near0 ? ch.y : ch.x;
+                cur = near0 ? ch.x : ch.y;
+            } else if (h0 || h1) {
+                cur = h0 ? ch.x : ch.y;
+            } else {
+                cur = sp > 0 ? stack[--sp] : INT_MIN;
+            }
+        }
+        // exact tests, one shape type at a time across the warp
+        unsigned waiting = __ballot_sync(0xffffffffu, pending >= 0);
+        if (waiting == 0u) {
+            if (__all_sync(0xffffffffu, cur == INT_MIN)) break;
+            continue;
+        }
+        const int my_type = pending >= 0 ? ((sv.shape_meta((uint32_t)pending).z >> FLAG_TYPE_SHIFT) & 7) : -1;
+        while (waiting) {
+            const int leader = __ffs(waiting) - 1;
+            const int type = __shfl_sync(0xffffffffu, my_type, leader);
+            if (pending >= 0 && my_type == type) {
+                switch (type) {
+                case 0: test_shape<T, 0>(sv, (uint32_t)pending, ray, acc); break;
+                case 2: test_shape<T, 2>(sv, (uint32_t)pending, ray, acc); break;
+                case 3: if (FULL) test_shape<T, 3>(sv, (uint32_t)pending, ray, acc); break;
+                case 4: if (FULL) test_shape<T, 4>(sv, (uint32_t)pending, ray, acc); break;
+                case 5: if (FULL) test_shape<T, 5>(sv, (uint32_t)pending, ray, acc); break;
+                default: break;  // planes are never bounded
+                }
+                pending = -1;
+                // World::is_in_shadow (world.rs:106-111) is an `any`: the first blocker ends the walk
+                if (acc.mode == MODE_SHADOW && acc.best_pos >= 0) {
+                    cur = INT_MIN;
+                    sp = 0;
+                }
+            }
+            waiting = __ballot_sync(0xffffffffu, pending >= 0);
+        }
     }
 }
 
@@ -519,12 +615,6 @@ RT_DEV void trace(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
     }
 }
 
-RT_DEV int shape_type_of(const SceneLayout& L, uint32_t pos) {
-    int t = 0;
-#pragma unroll
-    for (int k = 1; k < NUM_SHAPE_TYPES; ++k) t += (pos >= L.type_begin[k]) ? 1 : 0;
-    return t;
-}
 
 // utils.rs:16-24
 template <typename T> RT_DEV bool coarse_eq(T a, T b) { return a == b || fabs(a - b) < Real<T>::eps(); }
@@ -626,7 +716,7 @@ enum : int { ST_FETCH = 0, ST_RADIANCE = 1, ST_CONTAINER = 2, ST_SHADOW = 3, ST_
 constexpr int TILE_W = 8, TILE_H = 4;   // a warp's 32 pixel slots = one 8x4 tile
 constexpr int CHUNK_SLOTS = 64;         // slots a warp takes from the global counter at a time
 
-template <typename T, int MAX_FRAMES, bool FULL>
+template <typename T, int MAX_FRAMES, bool FULL, bool BVH>
 __global__ void __launch_bounds__(RT_BLOCK_THREADS, RT_MIN_BLOCKS_PER_SM)
 render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, SceneLayout layout, CameraParams<T> cam,
               T* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8, unsigned long long* __restrict__ counters,
@@ -762,7 +852,8 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
         acc.c.all_pos = acc.c.excl_pos = -1;
         acc.c.all_t = acc.c.excl_t = T(0);
         acc.c.all_orig = acc.c.excl_orig = 0;
-        if (acc.mode != MODE_IDLE) trace<T, FULL>(sv, ray, acc);
+        if (acc.mode != MODE_IDLE) trace<T, FULL>(sv, ray, acc);  // flat lists (BVH scenes: the unbounded shapes)
+        if (BVH) trace_bvh<T, FULL>(sv, ray, acc);               // every lane takes part: warp votes inside
 
         // ---- phase C: consume the result ------------------------------------------------------------
         bool finish_hit = false;     // ComputedHit complete -> start the light loop
@@ -785,7 +876,7 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
                 // Intersection::prepare_computations, intersection.rs:21-31
                 V3<T> point = ray.o + ray.d * t_hit;
                 V3<T> local_point = mat_point(g, point);  // shape.rs:22-27
-                V3<T> local_normal = local_normal_at(sv, (uint32_t)hit_pos, shape_type_of(sv.L, (uint32_t)hit_pos), g, local_point);
+                V3<T> local_normal = local_normal_at(sv, (uint32_t)hit_pos, (meta.z >> FLAG_TYPE_SHIFT) & 7, g, local_point);
                 normal = normalized(mat_transposed_vector(g, local_normal));
                 eye = neg(ray.d);
                 if (dot(normal, eye) < T(0)) normal = neg(normal);

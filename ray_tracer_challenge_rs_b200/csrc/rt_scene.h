@@ -5,8 +5,12 @@
 // metadata, with the shapes grouped by type so that the intersection loops contain no dispatch:
 //
 //   real blob : [ shape geometry S x 16 ][ triangle data NT x 12 ][ materials M x 12 ]
-//               [ patterns Q x 18 ][ lights L x 6 ][ cull spheres S x 4 ]
-//   int  blob : [ shape meta S x 4 ][ material meta M x 2 ][ pattern meta Q x 4 ]
+//               [ patterns Q x 18 ][ lights L x 6 ][ cull spheres S x 4 ][ BVH node boxes N x 12 ]
+//   int  blob : [ shape meta S x 8 ][ material meta M x 2 ][ pattern meta Q x 4 ][ BVH children N x 2 ]
+//
+// Shape order.  Flat scenes (few bounded shapes): grouped by type, world order inside a type.
+// BVH scenes: first the UNBOUNDED shapes (planes, untruncated cylinders / cones) grouped by type —
+// `type_begin` describes only that prefix — then the bounded shapes in BVH leaf order.
 //
 // Both blobs are staged into shared memory by every CTA when they fit (always, for the shipped
 // scenes: <= 3 KB), otherwise they are read through L1/L2 from global memory.
@@ -24,12 +28,14 @@ constexpr int SHAPE_REALS = 16;
 constexpr int SHAPE_MIN = 12;
 constexpr int SHAPE_MAX = 13;
 
-// ---- shape meta record: 4 int32 ---------------------------------------------------------------
+// ---- shape meta record: 8 int32 (the first four are read as one int4) ---------------------------
 //  [0] orig index in world.shapes (tie-breaks, intersections.rs:13-18 + world.rs:34)
 //  [1] material index
-//  [2] flags
+//  [2] flags | (shape type << FLAG_TYPE_SHIFT)
 //  [3] eq_class (lowest orig index of a value-equal shape; intersection.rs:38,47)
-constexpr int SHAPE_INTS = 4;
+//  [4] triangle slot (index into the triangle records), -1 otherwise
+constexpr int SHAPE_INTS = 8;
+constexpr int FLAG_TYPE_SHIFT = 8;
 constexpr int FLAG_CLOSED = 1;        // cylinder.rs:14 / cone.rs:14
 constexpr int FLAG_CASTS_SHADOW = 2;  // material.casts_shadow of the shape's material (world.rs:108)
 // The refraction-container walk treats value-equal shapes as one (intersection.rs:47).  A class of
@@ -64,6 +70,13 @@ constexpr int LIGHT_REALS = 6;
 // skipping the exact test changes no result (rt_kernel.cuh, trace_type).
 constexpr int CULL_REALS = 4;
 
+// ---- BVH node (not in the reference; csrc/rt_bvh.h builds it): 12 reals = the two children's
+// inflated world-space boxes (lo[3], hi[3] each); 2 ints = child references, >= 0 an inner node,
+// < 0 the leaf shape at sorted position ~ref.  One shape per leaf.
+constexpr int BVH_REALS = 12;
+constexpr int BVH_INTS = 2;
+constexpr int BVH_MAX_DEPTH = 60;  // device traversal stack; the builder falls back to median splits to stay below
+
 constexpr int NUM_SHAPE_TYPES = 6;  // order = rtgpu_shape_type: sphere, plane, cube, cylinder, cone, triangle
 
 // What a kernel needs to find its way around the two blobs.  Passed by value as a kernel parameter.
@@ -71,8 +84,10 @@ struct SceneLayout {
     uint32_t n_shapes;
     uint32_t type_begin[NUM_SHAPE_TYPES + 1];  // sorted positions [type_begin[t], type_begin[t+1]) hold type t
     uint32_t n_materials, n_patterns, n_lights;
-    uint32_t tri_off, mat_off, pat_off, light_off, cull_off;  // offsets into the real blob, in reals
-    uint32_t mat_meta_off, pat_meta_off;            // offsets into the int blob, in int32
+    uint32_t tri_off, mat_off, pat_off, light_off, cull_off, bvh_off;  // offsets into the real blob, in reals
+    uint32_t mat_meta_off, pat_meta_off, bvh_meta_off;  // offsets into the int blob, in int32
+    uint32_t n_bvh_nodes;                           // 0: flat scene (every shape is in a type_begin range)
+    int32_t bvh_root;                               // root reference (>= 0 node, < 0 single leaf)
     uint32_t n_reals, n_ints;                       // blob sizes
     uint32_t in_shared;                             // 1: CTAs stage both blobs in shared memory
 };

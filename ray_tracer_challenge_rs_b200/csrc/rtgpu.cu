@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/rtgpu.h"
+#include "rt_bvh.h"
 #include "rt_kernel.cuh"
 #include "rt_scene.h"
 
@@ -50,6 +51,7 @@ struct PackedScene {
     std::vector<double> reals;
     std::vector<int> ints;
     rt::SceneLayout layout;
+    bool has_cyl_cone_tri = false;
 };
 
 int validate_scene(const rtgpu_scene* s) {
@@ -206,6 +208,74 @@ void bounding_sphere(const rtgpu_scene* s, uint32_t i, double out[4]) {
     out[3] = r * r;
 }
 
+// Conservative world-space box of a bounded shape; false = unbounded (planes, untruncated cylinders / cones,
+// degenerate transforms): such shapes stay in the flat always-tested list.
+bool bounding_box(const rtgpu_scene* s, uint32_t i, rt::Aabb* out) {
+    const int type = s->shape_type[i];
+    if (type == RTGPU_PLANE) return false;
+    double M[9], p0[3];
+    if (!invert_affine(s->shape_inv + (size_t)i * 12, M, p0)) return false;
+    rt::Aabb box;
+    box.reset();
+    auto add_local = [&](const double v[3]) {
+        double w[3];
+        mat3_apply(M, v, w);
+        const double p[3] = {p0[0] + w[0], p0[1] + w[1], p0[2] + w[2]};
+        box.grow_point(p);
+    };
+    if (type == RTGPU_SPHERE) {
+        // the extent of M * (unit sphere) along axis k is the norm of row k of M
+        for (int k = 0; k < 3; ++k) {
+            const double e = std::sqrt(M[k * 3] * M[k * 3] + M[k * 3 + 1] * M[k * 3 + 1] + M[k * 3 + 2] * M[k * 3 + 2]);
+            box.lo[k] = p0[k] - e;
+            box.hi[k] = p0[k] + e;
+        }
+    } else if (type == RTGPU_CUBE || type == RTGPU_CYLINDER || type == RTGPU_CONE) {
+        double ylo = -1.0, yhi = 1.0, r = 1.0;
+        if (type != RTGPU_CUBE) {
+            ylo = s->shape_min[i];
+            yhi = s->shape_max[i];
+            if (!(std::isfinite(ylo) && std::isfinite(yhi)) || std::fabs(ylo) > 1e150 || std::fabs(yhi) > 1e150 || !(ylo <= yhi)) return false;
+            if (type == RTGPU_CONE) r = std::max(std::fabs(ylo), std::fabs(yhi));  // radius |y| at height y
+        }
+        for (int c = 0; c < 8; ++c) {
+            const double v[3] = {(c & 1) ? r : -r, (c & 2) ? yhi : ylo, (c & 4) ? r : -r};
+            add_local(v);
+        }
+    } else {  // triangle
+        const size_t t = (size_t)s->shape_triangle[i] * 3;
+        double v[3][3];
+        for (int k = 0; k < 3; ++k) {
+            v[0][k] = s->tri_vertex_1[t + k];
+            v[1][k] = s->tri_vertex_1[t + k] + s->tri_edge_1[t + k];
+            v[2][k] = s->tri_vertex_1[t + k] + s->tri_edge_2[t + k];
+        }
+        for (int j = 0; j < 3; ++j) add_local(v[j]);
+    }
+    // inflate: relative to the box size and to the magnitude of its coordinates (>> f64 rounding of the slab test)
+    double size = 0.0, mag = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        size = std::max(size, box.hi[k] - box.lo[k]);
+        mag = std::max(mag, std::max(std::fabs(box.lo[k]), std::fabs(box.hi[k])));
+    }
+    const double pad = size * 1e-6 + mag * 1e-9 + 1e-300;
+    for (int k = 0; k < 3; ++k) {
+        box.lo[k] -= pad;
+        box.hi[k] += pad;
+        if (!std::isfinite(box.lo[k]) || !std::isfinite(box.hi[k])) return false;
+    }
+    *out = box;
+    return true;
+}
+
+// Scenes with at least this many bounded shapes are traversed through a BVH (RTGPU_BVH_MIN overrides;
+// 0 disables the hierarchy).
+uint32_t bvh_threshold() {
+    const char* e = getenv("RTGPU_BVH_MIN");
+    if (e && *e) return (uint32_t)strtoul(e, nullptr, 10);
+    return 32;
+}
+
 int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     int st = validate_scene(s);
     if (st != RTGPU_OK) return st;
@@ -217,17 +287,51 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     lay.n_patterns = Q;
     lay.n_lights = L;
 
-    // stable grouping by type: world order is kept inside a type (and carried as `orig` for tie-breaks)
+    // bounded shapes may go into a BVH; unbounded ones always stay in the flat per-type lists
+    std::vector<rt::Aabb> boxes(S);
+    std::vector<uint8_t> bounded(S, 0);
+    uint32_t n_bounded = 0;
+    for (uint32_t i = 0; i < S; ++i) {
+        bounded[i] = bounding_box(s, i, &boxes[i]) ? 1 : 0;
+        n_bounded += bounded[i];
+    }
+    const uint32_t threshold = bvh_threshold();
+    const bool use_bvh = threshold > 0 && n_bounded >= threshold;
+
+    // flat part: stable grouping by type, world order kept inside a type (and carried as `orig` for tie-breaks)
     std::vector<uint32_t> order;
     order.reserve(S);
-    uint32_t n_tri = 0;
     for (int t = 0; t < rt::NUM_SHAPE_TYPES; ++t) {
         lay.type_begin[t] = (uint32_t)order.size();
         for (uint32_t i = 0; i < S; ++i)
-            if (s->shape_type[i] == t) order.push_back(i);
+            if (s->shape_type[i] == t && !(use_bvh && bounded[i])) order.push_back(i);
     }
-    lay.type_begin[rt::NUM_SHAPE_TYPES] = S;
-    n_tri = lay.type_begin[6] - lay.type_begin[5];
+    lay.type_begin[rt::NUM_SHAPE_TYPES] = (uint32_t)order.size();
+    // BVH part: bounded shapes in depth-first leaf order
+    rt::Bvh bvh;
+    const uint32_t n_flat = (uint32_t)order.size();
+    if (use_bvh) {
+        std::vector<uint32_t> items;
+        std::vector<rt::Aabb> item_boxes;
+        items.reserve(n_bounded);
+        item_boxes.reserve(n_bounded);
+        for (uint32_t i = 0; i < S; ++i)
+            if (bounded[i]) {
+                items.push_back(i);
+                item_boxes.push_back(boxes[i]);
+            }
+        bvh = rt::build_bvh(item_boxes, rt::BVH_MAX_DEPTH);
+        if (bvh.max_depth >= rt::BVH_MAX_DEPTH) return fail(RTGPU_ERR_UNSUPPORTED, "BVH depth %d exceeds the device stack", bvh.max_depth);
+        for (uint32_t k = 0; k < bvh.leaf_order.size(); ++k) order.push_back(items[bvh.leaf_order[k]]);
+    }
+    uint32_t n_tri = 0;
+    for (uint32_t i = 0; i < S; ++i) {
+        n_tri += s->shape_type[i] == RTGPU_TRIANGLE ? 1u : 0u;
+        if (s->shape_type[i] >= RTGPU_CYLINDER) out->has_cyl_cone_tri = true;
+    }
+    const uint32_t n_nodes = (uint32_t)bvh.nodes.size();
+    lay.n_bvh_nodes = use_bvh ? std::max(n_nodes, 1u) : 0u;  // a single bounded shape still gets one (half-empty) node
+    lay.bvh_root = 0;
 
     // value-equal classes: size parity and highest member (rt_scene.h FLAG_CONTAINER_REP)
     std::vector<uint32_t> class_size(S, 0), class_last(S, 0);
@@ -241,18 +345,23 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     lay.pat_off = lay.mat_off + M * rt::MAT_REALS;
     lay.light_off = lay.pat_off + Q * rt::PAT_REALS;
     lay.cull_off = (lay.light_off + L * rt::LIGHT_REALS + 1u) & ~1u;  // 16-byte aligned records
-    lay.n_reals = lay.cull_off + S * rt::CULL_REALS;
+    lay.bvh_off = lay.cull_off + S * rt::CULL_REALS;
+    lay.n_reals = lay.bvh_off + lay.n_bvh_nodes * rt::BVH_REALS;
     lay.n_reals = (lay.n_reals + 1u) & ~1u;
     lay.mat_meta_off = S * rt::SHAPE_INTS;
     lay.pat_meta_off = lay.mat_meta_off + M * rt::MAT_INTS;
-    lay.n_ints = lay.pat_meta_off + Q * rt::PAT_INTS;
+    lay.bvh_meta_off = (lay.pat_meta_off + Q * rt::PAT_INTS + 1u) & ~1u;
+    lay.n_ints = lay.bvh_meta_off + lay.n_bvh_nodes * rt::BVH_INTS;
     lay.n_ints = (lay.n_ints + 3u) & ~3u;
+    if ((uint64_t)S * rt::SHAPE_REALS + (uint64_t)n_tri * rt::TRI_REALS + (uint64_t)S * rt::CULL_REALS + (uint64_t)lay.n_bvh_nodes * rt::BVH_REALS > 0xF0000000ull)
+        return fail(RTGPU_ERR_UNSUPPORTED, "scene too large for 32-bit blob offsets (%u shapes)", S);
 
     out->reals.assign(lay.n_reals, 0.0);
     out->ints.assign(lay.n_ints, 0);
     double* R = out->reals.data();
     int* I = out->ints.data();
 
+    uint32_t tri_slot = 0;
     for (uint32_t pos = 0; pos < S; ++pos) {
         const uint32_t i = order[pos];
         double* g = R + (size_t)pos * rt::SHAPE_REALS;
@@ -265,15 +374,19 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
         if (s->shape_closed[i]) flags |= rt::FLAG_CLOSED;
         if (s->mat_casts_shadow[mat]) flags |= rt::FLAG_CASTS_SHADOW;
         if ((class_size[cls] & 1u) && class_last[cls] == i) flags |= rt::FLAG_CONTAINER_REP;
+        flags |= (int)s->shape_type[i] << rt::FLAG_TYPE_SHIFT;
         int* m = I + (size_t)pos * rt::SHAPE_INTS;
         m[0] = (int)i;
         m[1] = (int)mat;
         m[2] = flags;
         m[3] = (int)cls;
+        m[4] = -1;
         bounding_sphere(s, i, R + lay.cull_off + (size_t)pos * rt::CULL_REALS);
         if (s->shape_type[i] == RTGPU_TRIANGLE) {
             const size_t t = (size_t)s->shape_triangle[i] * 3;
-            double* td = R + lay.tri_off + (size_t)(pos - lay.type_begin[5]) * rt::TRI_REALS;
+            m[4] = (int)tri_slot;
+            double* td = R + lay.tri_off + (size_t)tri_slot * rt::TRI_REALS;
+            ++tri_slot;
             memcpy(td + 0, s->tri_vertex_1 + t, 3 * sizeof(double));
             memcpy(td + 3, s->tri_edge_1 + t, 3 * sizeof(double));
             memcpy(td + 6, s->tri_edge_2 + t, 3 * sizeof(double));
@@ -301,6 +414,33 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
         double* d = R + lay.light_off + (size_t)l * rt::LIGHT_REALS;
         memcpy(d, s->light_position + (size_t)l * 3, 3 * sizeof(double));
         memcpy(d + 3, s->light_intensity + (size_t)l * 3, 3 * sizeof(double));
+    }
+    if (use_bvh) {
+        const double inf = std::numeric_limits<double>::infinity();
+        auto leaf_ref = [&](int32_t ref) { return ref >= 0 ? ref : ~(int32_t)(n_flat + (uint32_t)(~ref)); };  // leaf k -> sorted position
+        if (n_nodes == 0) {
+            // one bounded shape: a node whose second child is an empty box
+            double* nb = R + lay.bvh_off;
+            const rt::Aabb& b = boxes[order[n_flat]];
+            for (int k = 0; k < 3; ++k) {
+                nb[k] = b.lo[k];
+                nb[3 + k] = b.hi[k];
+                nb[6 + k] = inf;
+                nb[9 + k] = -inf;
+            }
+            I[lay.bvh_meta_off + 0] = ~(int32_t)n_flat;
+            I[lay.bvh_meta_off + 1] = ~(int32_t)n_flat;
+        }
+        for (uint32_t k = 0; k < n_nodes; ++k) {
+            double* nb = R + lay.bvh_off + (size_t)k * rt::BVH_REALS;
+            for (int c = 0; c < 2; ++c)
+                for (int a = 0; a < 3; ++a) {
+                    nb[c * 6 + a] = bvh.nodes[k].box[c].lo[a];
+                    nb[c * 6 + 3 + a] = bvh.nodes[k].box[c].hi[a];
+                }
+            I[lay.bvh_meta_off + k * rt::BVH_INTS + 0] = leaf_ref(bvh.nodes[k].child[0]);
+            I[lay.bvh_meta_off + k * rt::BVH_INTS + 1] = leaf_ref(bvh.nodes[k].child[1]);
+        }
     }
     return RTGPU_OK;
 }
@@ -356,14 +496,15 @@ struct rtgpu_context {
     size_t d_out8_bytes = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
+    bool has_cyl_cone_tri = false;  // selects the kernel instantiated with those shape types
 };
 
 namespace {
 
-template <typename T, int MAX_FRAMES, bool FULL>
+template <typename T, int MAX_FRAMES, bool FULL, bool BVH>
 int launch_kernel_impl(rtgpu_context* ctx, const T* d_reals, const rt::CameraParams<T>& cam, T* d_out, uint8_t* d_out8,
                        unsigned long long* d_counters, cudaStream_t stream) {
-    auto kernel = rt::render_kernel<T, MAX_FRAMES, FULL>;
+    auto kernel = rt::render_kernel<T, MAX_FRAMES, FULL, BVH>;
     rt::SceneLayout lay = ctx->layout;
     size_t smem = (((size_t)lay.n_reals * sizeof(T) + 15) & ~size_t(15)) + (size_t)lay.n_ints * sizeof(int);
     // keep at least ~3 CTAs of 128 threads per SM resident: stage in shared memory only when small enough
@@ -391,9 +532,14 @@ template <typename T, int MAX_FRAMES>
 int launch_kernel(rtgpu_context* ctx, const T* d_reals, const rt::CameraParams<T>& cam, T* d_out, uint8_t* d_out8,
                   unsigned long long* d_counters, cudaStream_t stream) {
     // scenes without cylinders, cones and triangles run the kernel instantiated without those loops
-    const bool full = ctx->layout.type_begin[3] != ctx->layout.type_begin[6];
-    if (full) return launch_kernel_impl<T, MAX_FRAMES, true>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
-    return launch_kernel_impl<T, MAX_FRAMES, false>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    const bool full = ctx->has_cyl_cone_tri;
+    const bool bvh = ctx->layout.n_bvh_nodes > 0;
+    if (bvh) {
+        if (full) return launch_kernel_impl<T, MAX_FRAMES, true, true>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+        return launch_kernel_impl<T, MAX_FRAMES, false, true>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    }
+    if (full) return launch_kernel_impl<T, MAX_FRAMES, true, false>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    return launch_kernel_impl<T, MAX_FRAMES, false, false>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
 }
 
 template <typename T>
@@ -479,6 +625,7 @@ int upload_scene(rtgpu_context* ctx, const PackedScene& packed) {
     ctx->d_reals32 = nullptr;
     ctx->d_ints = nullptr;
     ctx->layout = lay;
+    ctx->has_cyl_cone_tri = packed.has_cyl_cone_tri;
     CUDA_TRY(cudaMalloc(&ctx->d_reals64, std::max<size_t>(16, (size_t)lay.n_reals * sizeof(double))));
     CUDA_TRY(cudaMalloc(&ctx->d_ints, std::max<size_t>(16, (size_t)lay.n_ints * sizeof(int))));
     if (lay.n_reals) CUDA_TRY(cudaMemcpyAsync(ctx->d_reals64, packed.reals.data(), (size_t)lay.n_reals * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));

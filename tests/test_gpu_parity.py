@@ -149,3 +149,54 @@ def test_f32_fast_mode_tolerance(name):
     frac = float((d <= 2).mean())
     print(f"f32 {name}: {frac * 100:.3f}% within 2 LSB, max {int(d.max())}")
     assert frac >= F32_BARS.get(name, 0.0), (name, frac)
+
+
+# ---------------------------------------------------------------------------------------------
+# BVH traversal (scenes with many bounded shapes).  RTGPU_BVH_MIN forces it on small scenes too.
+
+
+@pytest.fixture
+def force_bvh(monkeypatch):
+    monkeypatch.setenv("RTGPU_BVH_MIN", "1")
+
+
+@pytest.mark.parametrize("name", SHIPPED_SCENES)
+def test_bvh_shipped_scene_small(name, force_bvh):
+    flat, camera = load_scene_fixture(name)
+    cam = camera.resized(384, 384 * camera.vertical_size // camera.horizontal_size)
+    compare_with_oracle(flat, cam, label=f"bvh:{name}")
+
+
+@pytest.mark.parametrize("name", sorted(SPECIAL_WORLDS))
+def test_bvh_special_world(name, force_bvh):
+    world, camera = SPECIAL_WORLDS[name]()
+    compare_with_oracle(world.flatten(), camera, label=f"bvh:{name}")
+
+
+@pytest.mark.parametrize("name", ["cover", "table", "cylinders", "refraction"])
+def test_bvh_native_size_matches_reference_png(name, force_bvh):
+    flat, camera = load_scene_fixture(name)
+    canvas = render_gpu(camera, flat, want_rgb=False)
+    assert hashlib.sha256(np.ascontiguousarray(canvas.to_rgb8()).tobytes()).hexdigest() == INDEX[name]["sha256_rgb8"]
+
+
+def test_bvh_and_flat_traversal_agree_bit_for_bit(monkeypatch):
+    flat, camera = load_scene_fixture("reflect_refract")
+    cam = camera.resized(480, 320)
+    monkeypatch.setenv("RTGPU_BVH_MIN", "0")
+    a, sa = render_gpu(cam, flat, return_stats=True)
+    monkeypatch.setenv("RTGPU_BVH_MIN", "1")
+    b, sb = render_gpu(cam, flat, return_stats=True)
+    assert np.array_equal(a.pixels.view(np.uint64), b.pixels.view(np.uint64))
+    assert {k: sa[k] for k in COUNTERS} == {k: sb[k] for k in COUNTERS}
+
+
+@pytest.mark.parametrize("n_shapes,extent,size", [(40, 3.0, (160, 90)), (3000, 9.0, (192, 108)), (20000, 20.0, (128, 72))])
+def test_synthetic_scene_against_oracle(n_shapes, extent, size):
+    """BASELINE.json configs[4] at test scale: spheres + triangles, random materials / patterns, 2 lights."""
+    from ray_tracer_challenge_rs_b200.synthetic import synthetic_camera, synthetic_scene
+
+    flat = synthetic_scene(n_shapes, extent=extent)
+    cam = synthetic_camera(*size, distance=2.6 * extent)
+    n_differ, worst = compare_with_oracle(flat, cam, label=f"synthetic{n_shapes}")
+    print(f"synthetic {n_shapes}: {n_differ} pixels differ in f64 (max rel {worst:.2e})")
