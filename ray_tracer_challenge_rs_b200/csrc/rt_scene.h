@@ -8,9 +8,13 @@
 //               [ patterns Q x 18 ][ lights L x 6 ][ cull spheres S x 4 ][ BVH node boxes N x 12 ]
 //   int  blob : [ shape meta S x 8 ][ material meta M x 2 ][ pattern meta Q x 4 ][ BVH children N x 2 ]
 //
-// Shape order.  Flat scenes (few bounded shapes): grouped by type, world order inside a type.
-// BVH scenes: first the UNBOUNDED shapes (planes, untruncated cylinders / cones) grouped by type —
-// `type_begin` describes only that prefix — then the bounded shapes in BVH leaf order.
+// Shape order: [ uniform part ][ candidate part ].
+//   uniform part   : shapes every lane tests in lockstep, grouped by type (`type_begin`): the UNBOUNDED
+//                    shapes (planes, untruncated cylinders / cones); world order inside a type.
+//   candidate part : the bounded shapes.  Small scenes (<= 32 of them): grouped by type
+//                    (`mask_begin`, `mask_count`, `mask_type_bits`); each lane culls them against their
+//                    bounding spheres into a 32-bit candidate mask and only tests its own candidates.
+//                    Larger scenes: BVH leaf order (`n_bvh_nodes > 0`).
 //
 // Both blobs are staged into shared memory by every CTA when they fit (always, for the shipped
 // scenes: <= 3 KB), otherwise they are read through L1/L2 from global memory.
@@ -86,7 +90,9 @@ struct SceneLayout {
     uint32_t n_materials, n_patterns, n_lights;
     uint32_t tri_off, mat_off, pat_off, light_off, cull_off, bvh_off;  // offsets into the real blob, in reals
     uint32_t mat_meta_off, pat_meta_off, bvh_meta_off;  // offsets into the int blob, in int32
-    uint32_t n_bvh_nodes;                           // 0: flat scene (every shape is in a type_begin range)
+    uint32_t mask_begin, mask_count;                // candidate part of a small scene: positions [mask_begin, +mask_count), count <= 32
+    uint32_t mask_type_bits[NUM_SHAPE_TYPES];       // bit k set: candidate k (position mask_begin + k) has that type
+    uint32_t n_bvh_nodes;                           // > 0: the candidate part is a BVH
     int32_t bvh_root;                               // root reference (>= 0 node, < 0 single leaf)
     uint32_t n_reals, n_ints;                       // blob sizes
     uint32_t in_shared;                             // 1: CTAs stage both blobs in shared memory

@@ -297,6 +297,10 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     }
     const uint32_t threshold = bvh_threshold();
     const bool use_bvh = threshold > 0 && n_bounded >= threshold;
+    // few bounded shapes: per-lane candidate masks (<= 32 bits); RTGPU_BVH_MIN=0 with more than 32 bounded
+    // shapes falls back to testing everything in the uniform lists (with the bounding-sphere pre-test)
+    const char* mask_env = getenv("RTGPU_MASK");  // RTGPU_MASK=0: A/B switch back to the uniform lists
+    const bool use_mask = !use_bvh && n_bounded > 0 && n_bounded <= 32 && !(mask_env && mask_env[0] == '0');
 
     // flat part: stable grouping by type, world order kept inside a type (and carried as `orig` for tie-breaks)
     std::vector<uint32_t> order;
@@ -304,9 +308,19 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     for (int t = 0; t < rt::NUM_SHAPE_TYPES; ++t) {
         lay.type_begin[t] = (uint32_t)order.size();
         for (uint32_t i = 0; i < S; ++i)
-            if (s->shape_type[i] == t && !(use_bvh && bounded[i])) order.push_back(i);
+            if (s->shape_type[i] == t && !((use_bvh || use_mask) && bounded[i])) order.push_back(i);
     }
     lay.type_begin[rt::NUM_SHAPE_TYPES] = (uint32_t)order.size();
+    if (use_mask) {
+        lay.mask_begin = (uint32_t)order.size();
+        for (int t = 0; t < rt::NUM_SHAPE_TYPES; ++t)
+            for (uint32_t i = 0; i < S; ++i)
+                if (s->shape_type[i] == t && bounded[i]) {
+                    lay.mask_type_bits[t] |= 1u << (uint32_t)(order.size() - lay.mask_begin);
+                    order.push_back(i);
+                }
+        lay.mask_count = (uint32_t)order.size() - lay.mask_begin;
+    }
     // BVH part: bounded shapes in depth-first leaf order
     rt::Bvh bvh;
     const uint32_t n_flat = (uint32_t)order.size();

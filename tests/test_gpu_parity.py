@@ -191,6 +191,28 @@ def test_bvh_and_flat_traversal_agree_bit_for_bit(monkeypatch):
     assert {k: sa[k] for k in COUNTERS} == {k: sb[k] for k in COUNTERS}
 
 
+@pytest.mark.parametrize("env", [{"RTGPU_BVH_MIN": "0"}, {"RTGPU_BVH_MIN": "0", "RTGPU_MASK": "0"}])
+@pytest.mark.parametrize("name", ["cover", "cylinders", "all_shapes", "duplicate_glass"])
+def test_flat_traversal_variants(name, env, monkeypatch):
+    """Small scenes: per-lane candidate masks (default) and the uniform lists with bounding-sphere pre-test."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    if name in SPECIAL_WORLDS:
+        world, cam = SPECIAL_WORLDS[name]()
+        flat = world.flatten()
+    else:
+        flat, camera = load_scene_fixture(name)
+        cam = camera.resized(256, 256 * camera.vertical_size // camera.horizontal_size)
+    compare_with_oracle(flat, cam, label=f"{name}:{env}")
+
+
+def test_uniform_lists_with_many_bounded_shapes(monkeypatch):
+    monkeypatch.setenv("RTGPU_BVH_MIN", "0")  # no hierarchy, > 32 bounded shapes -> uniform lists
+    from ray_tracer_challenge_rs_b200.synthetic import synthetic_camera, synthetic_scene
+
+    compare_with_oracle(synthetic_scene(300, extent=4.0), synthetic_camera(96, 54, distance=11.0), label="uniform300")
+
+
 @pytest.mark.parametrize("n_shapes,extent,size", [(40, 3.0, (160, 90)), (3000, 9.0, (192, 108)), (20000, 20.0, (128, 72))])
 def test_synthetic_scene_against_oracle(n_shapes, extent, size):
     """BASELINE.json configs[4] at test scale: spheres + triangles, random materials / patterns, 2 lights."""
