@@ -225,6 +225,14 @@ int rtgpu_context_render(rtgpu_context *context, const rtgpu_camera *camera, con
                          const rtgpu_rows *rows, double *out_rgb, uint8_t *out_rgb8,
                          rtgpu_stats *stats);
 
+/* -- pinned host memory ---------------------------------------------------------------------- */
+/* Page-locked, device-mapped host memory.  When out_rgb / out_rgb8 of a host-buffer render live in such
+ * memory (these functions, cudaHostAlloc, cudaHostRegister, torch pin_memory ...) the kernels write the
+ * finished pixels straight into them over PCIe while the render is still running (no staging copy);
+ * ordinary pageable buffers work too, through a device staging buffer and a copy. */
+void *rtgpu_host_alloc(size_t bytes);
+void rtgpu_host_free(void *ptr);
+
 /* -- measurement helpers ------------------------------------------------------------------- */
 /* Dependent-free DFMA / FFMA chains on every SM: the measured FP64 / FP32 FMA-pipe peak that the
  * roofline of this path is quoted against (MEASURED_PEAKS.json has HBM and bf16 only).

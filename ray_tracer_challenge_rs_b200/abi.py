@@ -130,6 +130,8 @@ EXPORTED_SYMBOLS = (
     "rtgpu_context_destroy",
     "rtgpu_context_render_device",
     "rtgpu_context_render",
+    "rtgpu_host_alloc",
+    "rtgpu_host_free",
     "rtgpu_measure_fma_peak",
     "rtgpu_selftest_arith",
 )
@@ -204,6 +206,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     ]
     lib.rtgpu_measure_fma_peak.restype = C.c_int
     lib.rtgpu_measure_fma_peak.argtypes = [C.c_int, C.c_uint32, _pd, _pd]
+    lib.rtgpu_host_alloc.restype = C.c_void_p
+    lib.rtgpu_host_alloc.argtypes = [C.c_size_t]
+    lib.rtgpu_host_free.restype = None
+    lib.rtgpu_host_free.argtypes = [C.c_void_p]
     lib.rtgpu_selftest_arith.restype = C.c_int
     lib.rtgpu_selftest_arith.argtypes = [C.c_int, _pd, _pd, C.c_size_t, _pu64, _pu64, _pu64, _pu64]
     if lib.rtgpu_abi_version() != ABI_VERSION:

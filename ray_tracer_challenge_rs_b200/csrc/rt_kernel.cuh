@@ -514,60 +514,6 @@ RT_DEV void trace_type(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& a
     }
 }
 
-// ---- candidate masks (scenes with at most 32 bounded shapes) --------------------------------------
-// Lanes of a warp trace unrelated rays (different pixels, bounces, query kinds), so "skip the shape if
-// no lane needs it" almost never skips anything.  Instead every lane first culls ALL bounded shapes
-// against their bounding spheres (branch-free, converged) into its own bit mask, then the warp walks
-// the shape TYPES in order and, per step, every lane tests its own next candidate of that type: the
-// lanes run the same code on different shapes.  Steps per type = the largest candidate count of any
-// lane, not the number of shapes some lane needs.
-template <typename T>
-RT_DEV uint32_t cull_candidates(const SceneView<T>& sv, const Ray<T>& ray, const TraceAcc<T>& acc) {
-    uint32_t mask = 0;
-    const uint32_t n = sv.L.mask_count, base = sv.L.mask_begin;
-    for (uint32_t k = 0; k < n; ++k) {
-        const T* cs = sv.cull(base + k);  // see trace_type for the derivation of the test
-        const T ocx = cs[0] - ray.o.x, ocy = cs[1] - ray.o.y, ocz = cs[2] - ray.o.z;
-        const T bq = fma(ocz, ray.d.z, fma(ocy, ray.d.y, ocx * ray.d.x));
-        const T c2 = fma(ocz, ocz, fma(ocy, ocy, ocx * ocx));
-        const T ex = fma(c2, Real<T>::cull_shrink(), -cs[3]);
-        const bool culled = ex > T(0) && ((acc.mode != MODE_CONTAINER && bq < T(0)) || ex * acc.dir_sq > bq * bq);
-        mask |= culled ? 0u : (1u << k);
-    }
-    return mask;
-}
-
-template <typename T, int TYPE>
-RT_DEV void test_candidates(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& acc, uint32_t mask) {
-    uint32_t mine = mask & sv.L.mask_type_bits[TYPE];
-    while (__any_sync(0xffffffffu, mine != 0u)) {
-        if (mine) {
-            const uint32_t k = (uint32_t)__ffs((int)mine) - 1u;
-            mine &= mine - 1u;
-            test_shape<T, TYPE>(sv, sv.L.mask_begin + k, ray, acc);
-            // World::is_in_shadow is an `any` (world.rs:106-111): the first blocker settles a shadow query
-            if (acc.mode == MODE_SHADOW && acc.best_pos >= 0) mine = 0u;
-        }
-    }
-}
-
-template <typename T, bool FULL>
-RT_DEV void trace_candidates(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
-    uint32_t mask = (acc.mode != MODE_IDLE) ? cull_candidates(sv, ray, acc) : 0u;
-    if (acc.mode == MODE_SHADOW && acc.best_pos >= 0) mask = 0u;  // already blocked by an unbounded shape
-    test_candidates<T, 0>(sv, ray, acc, mask);
-    if (acc.mode == MODE_SHADOW && acc.best_pos >= 0) mask = 0u;
-    test_candidates<T, 2>(sv, ray, acc, mask);
-    if (FULL) {
-        if (acc.mode == MODE_SHADOW && acc.best_pos >= 0) mask = 0u;
-        test_candidates<T, 3>(sv, ray, acc, mask);
-        if (acc.mode == MODE_SHADOW && acc.best_pos >= 0) mask = 0u;
-        test_candidates<T, 4>(sv, ray, acc, mask);
-        if (acc.mode == MODE_SHADOW && acc.best_pos >= 0) mask = 0u;
-        test_candidates<T, 5>(sv, ray, acc, mask);
-    }
-}
-
 // ---- BVH traversal (scenes with many bounded shapes; rt_bvh.h) -----------------------------------
 // Each lane walks the hierarchy with its own small stack.  A child is entered iff the ray's parameter
 // interval inside its (inflated) box meets the interval the query still cares about:
@@ -759,6 +705,10 @@ enum : int { ST_FETCH = 0, ST_RADIANCE = 1, ST_CONTAINER = 2, ST_SHADOW = 3, ST_
 #define RT_MIN_BLOCKS_PER_SM 4
 #endif
 
+#ifndef RT_PHASE_SYNC
+#define RT_PHASE_SYNC 0
+#endif
+
 #ifndef RT_TILE_ORDER
 // 0 scanline, 1 middle-out, 2 bottom-up, 3 scattered.  Per-pixel cost varies by 50x and is spatially
 // clustered; in scanline order the expensive rows of a typical frame (floor reflections, glass) come
@@ -877,7 +827,7 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
                             V3<T> origin = ld3(cam.origin);
                             ray.o = origin;
                             ray.d = normalized(pixel - origin);
-                            out_index = (size_t)k * cam.hsize + x;
+                            out_index = (size_t)(cam.out_full_frame ? y : k) * cam.hsize + x;
                             depth = 0;
                             state = ST_RADIANCE;
                             ++c_primary;
@@ -891,7 +841,14 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
                 need = __ballot_sync(0xffffffffu, state == ST_FETCH);
             }
         }
+#if RT_PHASE_SYNC
+        // CTA-wide phase lockstep: every warp of the CTA traces, then every warp shades.  The kernel's
+        // code does not fit the instruction cache; keeping the warps of an SM in the same phase makes
+        // them share the lines they fetch.
+        if (__syncthreads_and(state == ST_DONE)) break;
+#else
         if (__all_sync(0xffffffffu, state == ST_DONE)) break;
+#endif
 
         // ---- phase B: one trace for every lane that has a ray ----------------------------------------
         TraceAcc<T> acc;
@@ -906,11 +863,12 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
         acc.c.all_pos = acc.c.excl_pos = -1;
         acc.c.all_t = acc.c.excl_t = T(0);
         acc.c.all_orig = acc.c.excl_orig = 0;
-        if (acc.mode != MODE_IDLE) trace<T, FULL>(sv, ray, acc);  // uniform lists: the unbounded shapes
-        // candidate part (every lane takes part: warp votes inside)
-        if (BVH) trace_bvh<T, FULL>(sv, ray, acc);
-        else if (sv.L.mask_count) trace_candidates<T, FULL>(sv, ray, acc);
+        if (acc.mode != MODE_IDLE) trace<T, FULL>(sv, ray, acc);  // uniform lists (BVH scenes: the unbounded shapes)
+        if (BVH) trace_bvh<T, FULL>(sv, ray, acc);  // every lane takes part: warp votes inside
 
+#if RT_PHASE_SYNC
+        __syncthreads();
+#endif
         // ---- phase C: consume the result ------------------------------------------------------------
         bool finish_hit = false;     // ComputedHit complete -> start the light loop
         bool after_lights = false;   // surface colour complete -> children

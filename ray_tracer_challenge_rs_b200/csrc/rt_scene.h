@@ -8,13 +8,11 @@
 //               [ patterns Q x 18 ][ lights L x 6 ][ cull spheres S x 4 ][ BVH node boxes N x 12 ]
 //   int  blob : [ shape meta S x 8 ][ material meta M x 2 ][ pattern meta Q x 4 ][ BVH children N x 2 ]
 //
-// Shape order: [ uniform part ][ candidate part ].
-//   uniform part   : shapes every lane tests in lockstep, grouped by type (`type_begin`): the UNBOUNDED
-//                    shapes (planes, untruncated cylinders / cones); world order inside a type.
-//   candidate part : the bounded shapes.  Small scenes (<= 32 of them): grouped by type
-//                    (`mask_begin`, `mask_count`, `mask_type_bits`); each lane culls them against their
-//                    bounding spheres into a 32-bit candidate mask and only tests its own candidates.
-//                    Larger scenes: BVH leaf order (`n_bvh_nodes > 0`).
+// Shape order: [ uniform part ][ BVH part ].
+//   uniform part : shapes every lane tests in lockstep, grouped by type (`type_begin`), world order inside
+//                  a type.  Small scenes: every shape (bounded ones behind a bounding-sphere pre-test).
+//                  BVH scenes: only the UNBOUNDED shapes (planes, untruncated cylinders / cones).
+//   BVH part     : the bounded shapes of a large scene, in BVH leaf order (`n_bvh_nodes > 0`).
 //
 // Both blobs are staged into shared memory by every CTA when they fit (always, for the shipped
 // scenes: <= 3 KB), otherwise they are read through L1/L2 from global memory.
@@ -90,9 +88,7 @@ struct SceneLayout {
     uint32_t n_materials, n_patterns, n_lights;
     uint32_t tri_off, mat_off, pat_off, light_off, cull_off, bvh_off;  // offsets into the real blob, in reals
     uint32_t mat_meta_off, pat_meta_off, bvh_meta_off;  // offsets into the int blob, in int32
-    uint32_t mask_begin, mask_count;                // candidate part of a small scene: positions [mask_begin, +mask_count), count <= 32
-    uint32_t mask_type_bits[NUM_SHAPE_TYPES];       // bit k set: candidate k (position mask_begin + k) has that type
-    uint32_t n_bvh_nodes;                           // > 0: the candidate part is a BVH
+    uint32_t n_bvh_nodes;                           // > 0: the bounded shapes are reached through a BVH
     int32_t bvh_root;                               // root reference (>= 0 node, < 0 single leaf)
     uint32_t n_reals, n_ints;                       // blob sizes
     uint32_t in_shared;                             // 1: CTAs stage both blobs in shared memory
@@ -110,6 +106,8 @@ struct CameraParams {
     uint32_t band_rows, shard_index, shard_count;
     uint32_t max_depth;  // World::MAX_REFLECTION_ITERATIONS (world.rs:15)
     uint32_t tile_stride;  // coprime to the number of 8x4 tiles: scattered tile order (rt_kernel.cuh)
+    uint32_t out_full_frame;  // 1: outputs are full-frame buffers indexed by image row (zero-copy into the
+                              //    caller's pinned host Canvas); 0: compact over the rows of this launch
 };
 
 // Work counters, in the order of the first six fields of rtgpu_stats.

@@ -297,30 +297,15 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     }
     const uint32_t threshold = bvh_threshold();
     const bool use_bvh = threshold > 0 && n_bounded >= threshold;
-    // few bounded shapes: per-lane candidate masks (<= 32 bits); RTGPU_BVH_MIN=0 with more than 32 bounded
-    // shapes falls back to testing everything in the uniform lists (with the bounding-sphere pre-test)
-    const char* mask_env = getenv("RTGPU_MASK");  // RTGPU_MASK=0: A/B switch back to the uniform lists
-    const bool use_mask = !use_bvh && n_bounded > 0 && n_bounded <= 32 && !(mask_env && mask_env[0] == '0');
-
     // flat part: stable grouping by type, world order kept inside a type (and carried as `orig` for tie-breaks)
     std::vector<uint32_t> order;
     order.reserve(S);
     for (int t = 0; t < rt::NUM_SHAPE_TYPES; ++t) {
         lay.type_begin[t] = (uint32_t)order.size();
         for (uint32_t i = 0; i < S; ++i)
-            if (s->shape_type[i] == t && !((use_bvh || use_mask) && bounded[i])) order.push_back(i);
+            if (s->shape_type[i] == t && !(use_bvh && bounded[i])) order.push_back(i);
     }
     lay.type_begin[rt::NUM_SHAPE_TYPES] = (uint32_t)order.size();
-    if (use_mask) {
-        lay.mask_begin = (uint32_t)order.size();
-        for (int t = 0; t < rt::NUM_SHAPE_TYPES; ++t)
-            for (uint32_t i = 0; i < S; ++i)
-                if (s->shape_type[i] == t && bounded[i]) {
-                    lay.mask_type_bits[t] |= 1u << (uint32_t)(order.size() - lay.mask_begin);
-                    order.push_back(i);
-                }
-        lay.mask_count = (uint32_t)order.size() - lay.mask_begin;
-    }
     // BVH part: bounded shapes in depth-first leaf order
     rt::Bvh bvh;
     const uint32_t n_flat = (uint32_t)order.size();
@@ -511,6 +496,8 @@ struct rtgpu_context {
     int sm_count = 0;
     size_t smem_optin = 0;
     bool has_cyl_cone_tri = false;  // selects the kernel instantiated with those shape types
+    size_t cap_reals = 0, cap_ints = 0;
+    bool zero_copy = false;  // the last host render wrote straight into the caller's pinned buffers
 };
 
 namespace {
@@ -557,7 +544,8 @@ int launch_kernel(rtgpu_context* ctx, const T* d_reals, const rt::CameraParams<T
 }
 
 template <typename T>
-void fill_camera(const rtgpu_camera* c, const RowSel& rows, uint32_t n_rows, uint32_t max_depth, rt::CameraParams<T>* out) {
+void fill_camera(const rtgpu_camera* c, const RowSel& rows, uint32_t n_rows, uint32_t max_depth, bool full_frame_out, rt::CameraParams<T>* out) {
+    out->out_full_frame = full_frame_out ? 1u : 0u;
     out->half_width = (T)c->half_width;
     out->half_height = (T)c->half_height;
     out->pixel_size = (T)c->pixel_size;
@@ -602,7 +590,8 @@ int check_opts(const rtgpu_opts* opts, uint32_t* precision, uint32_t* max_depth)
 }
 
 int render_device_impl(rtgpu_context* ctx, const rtgpu_camera* camera, const rtgpu_opts* opts, const rtgpu_rows* rows,
-                       void* d_out_rgb, uint8_t* d_out_rgb8, uint64_t* d_counters, cudaStream_t stream, uint32_t* out_n_rows) {
+                       void* d_out_rgb, uint8_t* d_out_rgb8, uint64_t* d_counters, cudaStream_t stream, uint32_t* out_n_rows,
+                       bool full_frame_out = false) {
     if (!ctx || !camera) return fail(RTGPU_ERR_INVALID_ARGUMENT, "context or camera is NULL");
     if (!d_out_rgb && !d_out_rgb8) return fail(RTGPU_ERR_INVALID_ARGUMENT, "both output pointers are NULL");
     uint32_t precision, max_depth;
@@ -618,30 +607,41 @@ int render_device_impl(rtgpu_context* ctx, const rtgpu_camera* camera, const rtg
     unsigned long long* counters = reinterpret_cast<unsigned long long*>(d_counters);
     if (precision == RTGPU_PRECISION_F64) {
         rt::CameraParams<double> cam;
-        fill_camera(camera, sel, n_rows, max_depth, &cam);
+        fill_camera(camera, sel, n_rows, max_depth, full_frame_out, &cam);
         if (max_depth <= 7) return launch_kernel<double, 8>(ctx, ctx->d_reals64, cam, (double*)d_out_rgb, d_out_rgb8, counters, stream);
         return launch_kernel<double, 16>(ctx, ctx->d_reals64, cam, (double*)d_out_rgb, d_out_rgb8, counters, stream);
     }
     st = ensure_f32_blob(ctx, stream);
     if (st != RTGPU_OK) return st;
     rt::CameraParams<float> cam;
-    fill_camera(camera, sel, n_rows, max_depth, &cam);
+    fill_camera(camera, sel, n_rows, max_depth, full_frame_out, &cam);
     if (max_depth <= 7) return launch_kernel<float, 8>(ctx, ctx->d_reals32, cam, (float*)d_out_rgb, d_out_rgb8, counters, stream);
     return launch_kernel<float, 16>(ctx, ctx->d_reals32, cam, (float*)d_out_rgb, d_out_rgb8, counters, stream);
 }
 
 int upload_scene(rtgpu_context* ctx, const PackedScene& packed) {
     const rt::SceneLayout& lay = packed.layout;
-    if (ctx->d_reals64) cudaFree(ctx->d_reals64);
-    if (ctx->d_reals32) cudaFree(ctx->d_reals32);
-    if (ctx->d_ints) cudaFree(ctx->d_ints);
-    ctx->d_reals64 = nullptr;
+    if (ctx->d_reals32) cudaFree(ctx->d_reals32);  // the f32 copy is rebuilt on demand
     ctx->d_reals32 = nullptr;
-    ctx->d_ints = nullptr;
     ctx->layout = lay;
     ctx->has_cyl_cone_tri = packed.has_cyl_cone_tri;
-    CUDA_TRY(cudaMalloc(&ctx->d_reals64, std::max<size_t>(16, (size_t)lay.n_reals * sizeof(double))));
-    CUDA_TRY(cudaMalloc(&ctx->d_ints, std::max<size_t>(16, (size_t)lay.n_ints * sizeof(int))));
+    // repeated frames of similar scenes reuse the allocations (cudaFree / cudaMalloc synchronise the device)
+    const size_t need_reals = std::max<size_t>(16, (size_t)lay.n_reals * sizeof(double));
+    const size_t need_ints = std::max<size_t>(16, (size_t)lay.n_ints * sizeof(int));
+    if (need_reals > ctx->cap_reals) {
+        if (ctx->d_reals64) cudaFree(ctx->d_reals64);
+        ctx->d_reals64 = nullptr;
+        ctx->cap_reals = 0;
+        CUDA_TRY(cudaMalloc(&ctx->d_reals64, need_reals));
+        ctx->cap_reals = need_reals;
+    }
+    if (need_ints > ctx->cap_ints) {
+        if (ctx->d_ints) cudaFree(ctx->d_ints);
+        ctx->d_ints = nullptr;
+        ctx->cap_ints = 0;
+        CUDA_TRY(cudaMalloc(&ctx->d_ints, need_ints));
+        ctx->cap_ints = need_ints;
+    }
     if (lay.n_reals) CUDA_TRY(cudaMemcpyAsync(ctx->d_reals64, packed.reals.data(), (size_t)lay.n_reals * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     if (lay.n_ints) CUDA_TRY(cudaMemcpyAsync(ctx->d_ints, packed.ints.data(), (size_t)lay.n_ints * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -703,6 +703,18 @@ int ensure_out_buffers(rtgpu_context* ctx, size_t rgb_bytes, size_t rgb8_bytes) 
     return RTGPU_OK;
 }
 
+// Device-side alias of a pinned, mapped host allocation (cudaHostAlloc / cudaHostRegister / torch pin_memory),
+// or nullptr for pageable memory.
+void* mapped_device_pointer(const void* host) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (attr.type != cudaMemoryTypeHost || attr.devicePointer == nullptr) return nullptr;
+    return attr.devicePointer;
+}
+
 // Issue (do not wait for) everything one device does for a host-buffer render: kernel + D2H of its
 // row bands into the full-frame host buffers.
 int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rtgpu_opts* opts, const rtgpu_rows* rows,
@@ -718,10 +730,26 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
     const size_t row_rgb = (size_t)camera->hsize * 3 * elem;
     const size_t row_rgb8 = (size_t)camera->hsize * 3;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    st = ensure_out_buffers(ctx, out_rgb ? row_rgb * n_rows : 0, out_rgb8 ? row_rgb8 * n_rows : 0);
-    if (st != RTGPU_OK) return st;
+    // Zero-copy: when the caller's buffers are pinned, device-mapped host memory the kernel writes each
+    // finished pixel straight into the caller's Canvas (full-frame indexing); the PCIe traffic then
+    // overlaps the render instead of following it.  Pageable buffers take the staging path below.
+    void* map_rgb = out_rgb ? mapped_device_pointer(out_rgb) : nullptr;
+    void* map_rgb8 = out_rgb8 ? mapped_device_pointer(out_rgb8) : nullptr;
+    const char* zc = getenv("RTGPU_ZEROCOPY");
+    ctx->zero_copy = !(zc && zc[0] == '0') && (!out_rgb || map_rgb) && (!out_rgb8 || map_rgb8);
+    if (!ctx->zero_copy) {
+        st = ensure_out_buffers(ctx, out_rgb ? row_rgb * n_rows : 0, out_rgb8 ? row_rgb8 * n_rows : 0);
+        if (st != RTGPU_OK) return st;
+    }
     CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, rt::NUM_COUNTERS * sizeof(unsigned long long), ctx->stream));
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (ctx->zero_copy) {
+        st = render_device_impl(ctx, camera, opts, rows, map_rgb, (uint8_t*)map_rgb8, reinterpret_cast<uint64_t*>(ctx->d_counters),
+                                ctx->stream, nullptr, /*full_frame_out=*/true);
+        if (st != RTGPU_OK) return st;
+        CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+        return RTGPU_OK;
+    }
     st = render_device_impl(ctx, camera, opts, rows, out_rgb ? ctx->d_out : nullptr, out_rgb8 ? ctx->d_out8 : nullptr,
                             reinterpret_cast<uint64_t*>(ctx->d_counters), ctx->stream, nullptr);
     if (st != RTGPU_OK) return st;
@@ -971,6 +999,24 @@ int rtgpu_render(const rtgpu_scene* scene, const rtgpu_camera* camera, const rtg
     }
     if (stats) stats->total_ms = wall_ms() - t0;
     return RTGPU_OK;
+}
+
+void* rtgpu_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (rtgpu_device_count() <= 0) {
+        fail(RTGPU_ERR_NO_DEVICE, "no CUDA device available");
+        return nullptr;
+    }
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+        cudaGetLastError();
+        fail(RTGPU_ERR_OUT_OF_MEMORY, "cudaHostAlloc(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+void rtgpu_host_free(void* ptr) {
+    if (ptr) cudaFreeHost(ptr);
 }
 
 int rtgpu_measure_fma_peak(int device, uint32_t precision, double* out_tflops, double* out_ms) {

@@ -160,6 +160,32 @@ class Renderer:
         abi.check(self._lib, st)
 
 
+class PinnedArray:
+    """A numpy array over ``rtgpu_host_alloc`` memory (page-locked, device-mapped): host-buffer renders
+    into it are zero-copy."""
+
+    def __init__(self, shape, dtype=np.float64):
+        self._lib = abi.load_library()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._ptr = self._lib.rtgpu_host_alloc(self.nbytes)
+        if not self._ptr:
+            raise abi.RtgpuError(abi.ERR_OUT_OF_MEMORY, (self._lib.rtgpu_last_error() or b"").decode())
+        buf = (C.c_char * self.nbytes).from_address(self._ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def close(self):
+        if self._ptr:
+            self.array = None
+            self._lib.rtgpu_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def measure_fma_peak(precision: str = "f64", device: int = 0) -> Tuple[float, float]:
     """(TFLOP/s, ms) of a dependent-free FMA chain on every SM — the FP-pipe roofline denominator."""
     lib = abi.load_library()
