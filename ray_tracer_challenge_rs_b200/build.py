@@ -65,7 +65,34 @@ def build(force: bool = False, extra_flags: Optional[List[str]] = None, verbose:
     return output
 
 
+HOST_DIR = os.path.join(PACKAGE_DIR, "host")
+HOST_CLI = os.path.join(HOST_DIR, "ray-tracer-cli")
+HOST_SOURCES = ["main.cpp", "scene_loader.cpp", "canvas.cpp"]
+HOST_HEADERS = ["rt_host.hpp", "scene_loader.hpp"]
+
+
+def build_host(force: bool = False) -> str:
+    """Compile the C++ host (`host/ray-tracer-cli`: YAML loader, World / Camera / Canvas mirror, flattener,
+    `--rendering-mode gpu`) against librtgpu.so.  -ffp-contract=off: the host math is bit-faithful."""
+    build()
+    deps = [os.path.join(HOST_DIR, f) for f in HOST_SOURCES + HOST_HEADERS] + [os.path.join(INCLUDE, "rtgpu.h"), OUTPUT]
+    if not force and os.path.exists(HOST_CLI) and all(os.path.getmtime(HOST_CLI) >= os.path.getmtime(d) for d in deps):
+        return HOST_CLI
+    gxx = shutil.which("g++")
+    if gxx is None:
+        raise RuntimeError("g++ not found")
+    cmd = [gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-Wall", "-Wextra", "-Wno-comment", "-o", HOST_CLI] + \
+          [os.path.join(HOST_DIR, s) for s in HOST_SOURCES] + ["-L", PACKAGE_DIR, "-lrtgpu", "-lz", "-Wl,-rpath,$ORIGIN/.."]
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    proc = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if proc.returncode != 0:
+        raise RuntimeError("host build failed:\n" + proc.stdout + proc.stderr)
+    return HOST_CLI
+
+
 if __name__ == "__main__":
     import sys
 
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_host(force="--force" in sys.argv))

@@ -235,3 +235,14 @@ def test_synthetic_scene_against_oracle(n_shapes, extent, size):
     cam = synthetic_camera(*size, distance=2.6 * extent)
     n_differ, worst = compare_with_oracle(flat, cam, label=f"synthetic{n_shapes}")
     print(f"synthetic {n_shapes}: {n_differ} pixels differ in f64 (max rel {worst:.2e})")
+
+
+@pytest.mark.parametrize("bvh_min", ["32", "1"])
+def test_showcase_yaml_scene(bvh_min, monkeypatch):
+    """tests/scenes/showcase.yaml through the loader: cones and cylinders from YAML, all four pattern kinds,
+    two lights, define / extend — flat traversal and BVH."""
+    from ray_tracer_challenge_rs_b200 import load_scene_description
+
+    monkeypatch.setenv("RTGPU_BVH_MIN", bvh_min)
+    world, camera = load_scene_description(os.path.join(os.path.dirname(os.path.abspath(__file__)), "scenes", "showcase.yaml"))
+    compare_with_oracle(world.flatten(), camera, label=f"showcase:bvh_min={bvh_min}")
