@@ -219,7 +219,40 @@ struct TraceAcc {
     ContainerAcc<T> c;
 };
 
+// The container query's bookkeeping for one shape (rare: only hits on transparent materials ask for
+// it), kept out of line so the three hot query loops stay small.
 template <typename T>
+RT_COLD void consume_container(ContainerAcc<T>& c, int n, T t0, T t1, T t2, T t3, int pos, int4 meta) {
+    const T ts[4] = {t0, t1, t2, t3};
+    int count = 0;
+    T tmax = -Real<T>::max();
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k < n && ts[k] < c.t_hit) {
+            ++count;
+            if (!any || ts[k] > tmax) tmax = ts[k];
+            any = true;
+        }
+    }
+    if (count & 1) {
+        if (meta.w == c.hit_class) {
+            c.hit_class_inside = true;
+        } else if (c.excl_pos < 0 || tmax > c.excl_t || (tmax == c.excl_t && meta.x > c.excl_orig)) {
+            c.excl_pos = pos;
+            c.excl_t = tmax;
+            c.excl_orig = meta.x;
+        }
+        if (c.all_pos < 0 || tmax > c.all_t || (tmax == c.all_t && meta.x > c.all_orig)) {
+            c.all_pos = pos;
+            c.all_t = tmax;
+            c.all_orig = meta.x;
+        }
+    }
+}
+
+// NMAX = the most intersections the shape type can push (sphere 2, plane 1, cube 2, cylinder / cone 4, triangle 1)
+template <typename T, int NMAX>
 RT_DEV void consume(TraceAcc<T>& a, int n, T t0, T t1, T t2, T t3, int pos, int4 meta) {
     if (a.mode != MODE_CONTAINER) {
         // intersections.rs:13-18 / intersection.rs:77-79.  NaN fails `t >= 0`.
@@ -227,7 +260,7 @@ RT_DEV void consume(TraceAcc<T>& a, int n, T t0, T t1, T t2, T t3, int pos, int4
         if (eligible) {
             const T ts[4] = {t0, t1, t2, t3};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < NMAX; ++k) {
                 if (k < n) {
                     T t = ts[k];
                     if (t >= T(0) && (t < a.best_t || (t == a.best_t && meta.x < a.best_orig))) {
@@ -239,32 +272,7 @@ RT_DEV void consume(TraceAcc<T>& a, int n, T t0, T t1, T t2, T t3, int pos, int4
             }
         }
     } else if (meta.z & FLAG_CONTAINER_REP) {
-        const T ts[4] = {t0, t1, t2, t3};
-        int count = 0;
-        T tmax = -Real<T>::max();
-        bool any = false;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (k < n && ts[k] < a.c.t_hit) {
-                ++count;
-                if (!any || ts[k] > tmax) tmax = ts[k];
-                any = true;
-            }
-        }
-        if (count & 1) {
-            if (meta.w == a.c.hit_class) {
-                a.c.hit_class_inside = true;
-            } else if (a.c.excl_pos < 0 || tmax > a.c.excl_t || (tmax == a.c.excl_t && meta.x > a.c.excl_orig)) {
-                a.c.excl_pos = pos;
-                a.c.excl_t = tmax;
-                a.c.excl_orig = meta.x;
-            }
-            if (a.c.all_pos < 0 || tmax > a.c.all_t || (tmax == a.c.all_t && meta.x > a.c.all_orig)) {
-                a.c.all_pos = pos;
-                a.c.all_t = tmax;
-                a.c.all_orig = meta.x;
-            }
-        }
+        consume_container(a.c, n, t0, t1, t2, t3, pos, meta);
     }
 }
 
@@ -289,7 +297,7 @@ RT_DEV bool solve_quadratic(T a, T b, T c, T& s1, T& s2) {
 
 // shapes/cube.rs:22-43, native operators (fallback of cube_axis_fast)
 template <typename T>
-RT_COLD void cube_check_axis(T origin, T direction, T& tmin, T& tmax) {
+RT_DEV void cube_check_axis_native(T origin, T direction, T& tmin, T& tmax) {
     T nmin = T(-1) - origin;
     T nmax = T(1) - origin;
     T dmin, dmax;
@@ -307,6 +315,13 @@ RT_COLD void cube_check_axis(T origin, T direction, T& tmin, T& tmax) {
     }
     tmin = dmin;
     tmax = dmax;
+}
+
+template <typename T>
+RT_COLD void cube_axes_native(const Ray<T>& r, T& xmin, T& xmax, T& ymin, T& ymax, T& zmin, T& zmax) {
+    cube_check_axis_native(r.o.x, r.d.x, xmin, xmax);
+    cube_check_axis_native(r.o.y, r.d.y, ymin, ymax);
+    cube_check_axis_native(r.o.z, r.d.z, zmin, zmax);
 }
 
 // shapes/cube.rs:22-43 without branches: both slab distances share one reciprocal; `ok` turns false
@@ -375,11 +390,7 @@ RT_DEV int local_intersect(const Ray<T>& r, const T* g, int flags, const T* tri,
         cube_axis_fast(r.o.x, r.d.x, xmin, xmax, ok);
         cube_axis_fast(r.o.y, r.d.y, ymin, ymax, ok);
         cube_axis_fast(r.o.z, r.d.z, zmin, zmax, ok);
-        if (!ok) {
-            cube_check_axis(r.o.x, r.d.x, xmin, xmax);
-            cube_check_axis(r.o.y, r.d.y, ymin, ymax);
-            cube_check_axis(r.o.z, r.d.z, zmin, zmax);
-        }
+        if (!ok) cube_axes_native(r, xmin, xmax, ymin, ymax, zmin, zmax);
         T dmin = fmax(fmax(fmax(-Real<T>::max(), xmin), ymin), zmin);
         T dmax = fmin(fmin(fmin(Real<T>::max(), xmax), ymax), zmax);
         if (dmin < dmax && dmax > T(0)) {
@@ -485,7 +496,8 @@ RT_DEV void test_shape(const SceneView<T>& sv, uint32_t pos, const Ray<T>& ray, 
     local.d = mat_vector(g, ray.d);
     T t0, t1, t2, t3;
     int n = local_intersect<T, TYPE>(local, g, meta.z, TYPE == 5 ? sv.triangle(pos) : nullptr, t0, t1, t2, t3);
-    consume(acc, n, t0, t1, t2, t3, (int)pos, meta);
+    constexpr int NMAX = (TYPE == 0 || TYPE == 2) ? 2 : (TYPE == 3 || TYPE == 4) ? 4 : 1;
+    consume<T, NMAX>(acc, n, t0, t1, t2, t3, (int)pos, meta);
 }
 
 // World::collect_intersections (world.rs:25-35) over the flat per-type lists: every shape, no dispatch.
@@ -930,7 +942,9 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
                     V3<T> diffuse = (effective * m[MAT_DIFFUSE]) * ldn;
                     V3<T> refl = reflect(neg(light_dir), normal);
                     T rde = dot(refl, eye);
-                    if (rde <= T(0)) {
+                    // specular == 0 (every matte material): (intensity * 0) * pow(..) is an exact zero for the
+                    // finite factor pow returns on (0, ~1], so the whole term — and the pow call — is skipped
+                    if (rde <= T(0) || m[MAT_SPECULAR] == T(0)) {
                         lit = ambient + diffuse;
                     } else {
                         T factor = pow(rde, m[MAT_SHININESS]);
