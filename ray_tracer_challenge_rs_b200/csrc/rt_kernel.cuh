@@ -613,6 +613,43 @@ RT_DEV void trace_bvh(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& ac
     }
 }
 
+// One loop over the uniform shape list with a warp-uniform switch on the shape type: the pre-test, the
+// object-space transform and the query bookkeeping exist ONCE in the instruction stream instead of once
+// per shape type.  The render kernel is bound by instruction-cache misses (GCC request rate), so code
+// bytes on the hot path matter more than the handful of extra instructions per shape.
+template <typename T, bool FULL>
+RT_DEV void trace_unified(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
+    const uint32_t n = sv.L.type_begin[NUM_SHAPE_TYPES];
+    for (uint32_t pos = 0; pos < n; ++pos) {
+#if RT_CULL
+        {
+            const T* cs = sv.cull(pos);  // see trace_type; unbounded shapes carry r2 = +inf and always pass
+            const T ocx = cs[0] - ray.o.x, ocy = cs[1] - ray.o.y, ocz = cs[2] - ray.o.z;
+            const T bq = fma(ocz, ray.d.z, fma(ocy, ray.d.y, ocx * ray.d.x));
+            const T c2 = fma(ocz, ocz, fma(ocy, ocy, ocx * ocx));
+            const T ex = fma(c2, Real<T>::cull_shrink(), -cs[3]);
+            if (ex > T(0) && ((acc.mode != MODE_CONTAINER && bq < T(0)) || ex * acc.dir_sq > bq * bq)) continue;
+        }
+#endif
+        const T* g = sv.shape(pos);
+        const int4 meta = sv.shape_meta(pos);
+        Ray<T> local;  // ray.rs:45-49
+        local.o = mat_point(g, ray.o);
+        local.d = mat_vector(g, ray.d);
+        T t0 = T(0), t1 = T(0), t2 = T(0), t3 = T(0);
+        int k = 0;
+        switch ((meta.z >> FLAG_TYPE_SHIFT) & 7) {
+        case 0: k = local_intersect<T, 0>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
+        case 1: k = local_intersect<T, 1>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
+        case 2: k = local_intersect<T, 2>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
+        case 3: if (FULL) k = local_intersect<T, 3>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
+        case 4: if (FULL) k = local_intersect<T, 4>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
+        default: if (FULL) k = local_intersect<T, 5>(local, g, meta.z, sv.triangle(pos), t0, t1, t2, t3); break;
+        }
+        consume<T, 4>(acc, k, t0, t1, t2, t3, (int)pos, meta);
+    }
+}
+
 // FULL = false: the scene holds only spheres, planes and cubes (all but one shipped scene); the
 // cylinder / cone / triangle loops are not even instantiated, which keeps the code footprint down.
 template <typename T, bool FULL>
@@ -715,6 +752,10 @@ enum : int { ST_FETCH = 0, ST_RADIANCE = 1, ST_CONTAINER = 2, ST_SHADOW = 3, ST_
 #endif
 #ifndef RT_MIN_BLOCKS_PER_SM
 #define RT_MIN_BLOCKS_PER_SM 4
+#endif
+
+#ifndef RT_UNIFIED_LOOP
+#define RT_UNIFIED_LOOP 1
 #endif
 
 #ifndef RT_PHASE_SYNC
@@ -875,7 +916,11 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
         acc.c.all_pos = acc.c.excl_pos = -1;
         acc.c.all_t = acc.c.excl_t = T(0);
         acc.c.all_orig = acc.c.excl_orig = 0;
+#if RT_UNIFIED_LOOP
+        if (acc.mode != MODE_IDLE) trace_unified<T, FULL>(sv, ray, acc);  // uniform list (BVH scenes: the unbounded shapes)
+#else
         if (acc.mode != MODE_IDLE) trace<T, FULL>(sv, ray, acc);  // uniform lists (BVH scenes: the unbounded shapes)
+#endif
         if (BVH) trace_bvh<T, FULL>(sv, ray, acc);  // every lane takes part: warp votes inside
 
 #if RT_PHASE_SYNC
