@@ -771,7 +771,10 @@ enum : int { ST_FETCH = 0, ST_RADIANCE = 1, ST_CONTAINER = 2, ST_SHADOW = 3, ST_
 #endif
 
 constexpr int TILE_W = 8, TILE_H = 4;   // a warp's 32 pixel slots = one 8x4 tile
-constexpr int CHUNK_SLOTS = 64;         // slots a warp takes from the global counter at a time
+#ifndef RT_CHUNK_SLOTS
+#define RT_CHUNK_SLOTS 64
+#endif
+constexpr int CHUNK_SLOTS = RT_CHUNK_SLOTS;  // slots a warp takes from the global counter at a time
 
 template <typename T, int MAX_FRAMES, bool FULL, bool BVH>
 __global__ void __launch_bounds__(RT_BLOCK_THREADS, RT_MIN_BLOCKS_PER_SM)
