@@ -745,7 +745,7 @@ struct Frame {
 };
 enum : int { FR_REFLECT = 1, FR_REFRACT = 2, FR_SCHLICK = 4, FR_WAIT_REFLECT = 8, FR_WAIT_REFRACT = 16 };
 
-enum : int { ST_FETCH = 0, ST_RADIANCE = 1, ST_CONTAINER = 2, ST_SHADOW = 3 };
+enum : int { ST_FETCH = 0, ST_RADIANCE = 1, ST_CONTAINER = 2, ST_SHADOW = 3, ST_DONE = 4 };
 
 #ifndef RT_BLOCK_THREADS
 #define RT_BLOCK_THREADS 128
@@ -776,60 +776,11 @@ constexpr int TILE_W = 8, TILE_H = 4;   // a warp's 32 pixel slots = one 8x4 til
 #endif
 constexpr int CHUNK_SLOTS = RT_CHUNK_SLOTS;  // slots a warp takes from the global counter at a time
 
-// A primary hit whose shading is postponed (see "heavy pixels first" in the kernel).
-template <typename T>
-struct Deferred {
-    T t;            // hit distance of the camera ray
-    int pos;        // sorted position of the hit shape
-    uint32_t slot;  // pixel slot (tile order) the camera ray belongs to
-};
-
-// Pixel slot -> pixel, camera ray (Camera::ray_for_pixel, camera.rs:52-68) and output index.
-// false: the slot is padding of a partial tile.
-template <typename T>
-RT_COLD bool pixel_from_slot(const CameraParams<T>& cam, uint32_t tiles_x, uint32_t tiles_y, uint32_t slot, Ray<T>& ray, size_t& out_index) {
-    uint32_t tile = slot / (TILE_W * TILE_H), in = slot % (TILE_W * TILE_H);
-    uint32_t tile_row = tile / tiles_x;
-#if RT_TILE_ORDER == 1
-    // rows of tiles from the middle of the frame outwards
-    {
-        const uint32_t mid = tiles_y / 2;
-        const uint32_t h = (tile_row + 1) / 2;
-        tile_row = (tile_row & 1u) ? (mid >= h ? mid - h : tiles_y - 1 - (h - mid - 1)) : (mid + h < tiles_y ? mid + h : (tiles_y - 1) - (mid + h - tiles_y));
-    }
-#elif RT_TILE_ORDER == 2
-    tile_row = tiles_y - 1 - tile_row;  // bottom-up (experiment)
-#elif RT_TILE_ORDER == 3
-    // scattered: a multiplicative permutation of the tile index (stride coprime to the tile count), so
-    // that every part of the frame is sampled all along the launch
-    {
-        const uint32_t n_tiles = tiles_x * tiles_y;
-        tile = (uint32_t)(((unsigned long long)tile * cam.tile_stride) % n_tiles);
-        tile_row = tile / tiles_x;
-    }
-#endif
-    const uint32_t x = (tile % tiles_x) * TILE_W + in % TILE_W;
-    const uint32_t k = tile_row * TILE_H + in / TILE_W;
-    if (!(x < cam.hsize && k < cam.n_rows)) return false;
-    const uint32_t y = ((k / cam.band_rows) * cam.shard_count + cam.shard_index) * cam.band_rows + k % cam.band_rows;
-    // Camera::ray_for_pixel, camera.rs:52-68
-    T offset_x = (T(x) + T(0.5)) * cam.pixel_size;
-    T offset_y = (T(y) + T(0.5)) * cam.pixel_size;
-    T world_x = cam.half_width - offset_x;
-    T world_y = cam.half_height - offset_y;
-    V3<T> pixel = mat_point(cam.inv, mk<T>(world_x, world_y, T(-1)));
-    V3<T> origin = ld3(cam.origin);
-    ray.o = origin;
-    ray.d = normalized(pixel - origin);
-    out_index = (size_t)(cam.out_full_frame ? y : k) * cam.hsize + x;
-    return true;
-}
-
 template <typename T, int MAX_FRAMES, bool FULL, bool BVH>
 __global__ void __launch_bounds__(RT_BLOCK_THREADS, RT_MIN_BLOCKS_PER_SM)
 render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, SceneLayout layout, CameraParams<T> cam,
               T* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8, unsigned long long* __restrict__ counters,
-              unsigned int* __restrict__ work_counter, Deferred<T>* __restrict__ defer_base, uint32_t defer_cap) {
+              unsigned int* __restrict__ work_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SceneView<T> sv;
     sv.L = layout;
@@ -869,26 +820,14 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
     // warp-private chunk of pixel slots
     uint32_t chunk_next = 0, chunk_end = 0;
     bool exhausted = false;
-    // Heavy pixels first.  A pixel is evaluated by one lane, sequentially, and a camera ray that hits a
-    // transparent surface can grow a tree of ~100 rays while most pixels need 3-20: if such a pixel starts
-    // late, the whole launch waits for it.  So in the first sweep over the frame a lane only FINISHES the
-    // pixels whose camera ray hits a transparent material; for every other pixel it parks the primary hit
-    // (distance, shape) in its warp's ring and moves on.  When the frame has no unvisited pixel left the
-    // warp drains its ring, resuming each parked pixel at its hit.  Nothing is traced twice and the
-    // arithmetic of a pixel is unchanged; only the order in which pixels are shaded differs.
-    Deferred<T>* const ring = defer_base ? defer_base + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * defer_cap : nullptr;
-    uint32_t ring_count = 0, ring_next = 0;  // warp-uniform
-    uint32_t cur_slot = 0;
-    bool primary = false;   // the radiance ray in flight is a first-sweep camera ray
-    int resume_pos = -1;    // >= 0: this lane resumes a parked pixel, no trace needed
-    T resume_t = T(0);
     // counters
     unsigned int c_primary = 0, c_shadow = 0, c_reflect = 0, c_refract = 0, c_nodes = 0;
 
     for (;;) {
-        // ---- phase A: idle lanes take the next pixel slot of the warp's chunk, then the parked pixels ----
+        // ---- phase A: idle lanes take the next pixel slot of the warp's chunk ---------------------
         {
-            unsigned need = exhausted ? 0u : __ballot_sync(0xffffffffu, state == ST_FETCH);
+            if (exhausted && state == ST_FETCH) state = ST_DONE;
+            unsigned need = __ballot_sync(0xffffffffu, state == ST_FETCH);
             while (need) {
                 if (chunk_next >= chunk_end) {
                     uint32_t base_slot = 0;
@@ -896,62 +835,80 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
                     base_slot = __shfl_sync(0xffffffffu, base_slot, 0);
                     chunk_next = base_slot;
                     chunk_end = base_slot + CHUNK_SLOTS;
-                    if (base_slot >= total_slots) {  // no unvisited pixel left in the frame
+                    if (base_slot >= total_slots) {  // frame exhausted
+                        if (state == ST_FETCH) state = ST_DONE;
                         exhausted = true;
                         break;
                     }
                 }
                 unsigned rank = __popc(need & ((1u << lane) - 1u));
                 uint32_t avail = chunk_end - chunk_next;
-                if (state == ST_FETCH && rank < avail) {
-                    const uint32_t slot = chunk_next + rank;
-                    if (slot < total_slots && pixel_from_slot(cam, tiles_x, tiles_y, slot, ray, out_index)) {
-                        cur_slot = slot;
-                        depth = 0;
-                        state = ST_RADIANCE;
-                        primary = true;
-                        resume_pos = -1;
-                        ++c_primary;
-                    }  // else: padding slot, try again on the next round
+                bool mine = (state == ST_FETCH) && rank < avail;
+                if (mine) {
+                    uint32_t slot = chunk_next + rank;
+                    state = ST_DONE;  // unless the slot is a real pixel
+                    if (slot < total_slots) {
+                        uint32_t tile = slot / (TILE_W * TILE_H), in = slot % (TILE_W * TILE_H);
+                        uint32_t tile_row = tile / tiles_x;
+#if RT_TILE_ORDER == 1
+                        // rows of tiles from the middle of the frame outwards: the expensive pixels of a
+                        // typical scene (glass, mirrors) sit near the centre and should start first
+                        {
+                            const uint32_t mid = tiles_y / 2;
+                            const uint32_t h = (tile_row + 1) / 2;
+                            tile_row = (tile_row & 1u) ? (mid >= h ? mid - h : tiles_y - 1 - (h - mid - 1)) : (mid + h < tiles_y ? mid + h : (tiles_y - 1) - (mid + h - tiles_y));
+                        }
+#elif RT_TILE_ORDER == 2
+                        tile_row = tiles_y - 1 - tile_row;  // bottom-up (experiment)
+#elif RT_TILE_ORDER == 3
+                        // scattered: a multiplicative permutation of the tile index (stride coprime to the
+                        // tile count), so that every part of the frame is sampled all along the launch
+                        {
+                            const uint32_t n_tiles = tiles_x * tiles_y;
+                            tile = (uint32_t)(((unsigned long long)tile * cam.tile_stride) % n_tiles);
+                            tile_row = tile / tiles_x;
+                        }
+#endif
+                        uint32_t x = (tile % tiles_x) * TILE_W + in % TILE_W;
+                        uint32_t k = tile_row * TILE_H + in / TILE_W;
+                        state = ST_FETCH;  // padding slot: try again on the next round
+                        if (x < cam.hsize && k < cam.n_rows) {
+                            uint32_t y = ((k / cam.band_rows) * cam.shard_count + cam.shard_index) * cam.band_rows + k % cam.band_rows;
+                            // Camera::ray_for_pixel, camera.rs:52-68
+                            T offset_x = (T(x) + T(0.5)) * cam.pixel_size;
+                            T offset_y = (T(y) + T(0.5)) * cam.pixel_size;
+                            T world_x = cam.half_width - offset_x;
+                            T world_y = cam.half_height - offset_y;
+                            V3<T> pixel = mat_point(cam.inv, mk<T>(world_x, world_y, T(-1)));
+                            V3<T> origin = ld3(cam.origin);
+                            ray.o = origin;
+                            ray.d = normalized(pixel - origin);
+                            out_index = (size_t)(cam.out_full_frame ? y : k) * cam.hsize + x;
+                            depth = 0;
+                            state = ST_RADIANCE;
+                            ++c_primary;
+                        }
+                    } else {
+                        state = ST_DONE;
+                    }
                 }
                 uint32_t taken = min(avail, (uint32_t)__popc(need));
                 chunk_next += taken;
                 need = __ballot_sync(0xffffffffu, state == ST_FETCH);
             }
-            if (exhausted) {
-                // second sweep: parked pixels of this warp
-                unsigned want = __ballot_sync(0xffffffffu, state == ST_FETCH);
-                if (want && ring_next < ring_count) {
-                    unsigned rank = __popc(want & ((1u << lane) - 1u));
-                    uint32_t avail = ring_count - ring_next;
-                    if (state == ST_FETCH && rank < avail) {
-                        const Deferred<T> d = ring[ring_next + rank];
-                        pixel_from_slot(cam, tiles_x, tiles_y, d.slot, ray, out_index);
-                        cur_slot = d.slot;
-                        depth = 0;
-                        state = ST_RADIANCE;
-                        primary = false;
-                        resume_pos = d.pos;
-                        resume_t = d.t;
-                    }
-                    ring_next += min(avail, (uint32_t)__popc(want));
-                }
-            }
         }
-        const bool warp_idle = exhausted && ring_next >= ring_count && __all_sync(0xffffffffu, state == ST_FETCH);
 #if RT_PHASE_SYNC
         // CTA-wide phase lockstep: every warp of the CTA traces, then every warp shades.  The kernel's
         // code does not fit the instruction cache; keeping the warps of an SM in the same phase makes
         // them share the lines they fetch.
-        if (__syncthreads_and(warp_idle)) break;
+        if (__syncthreads_and(state == ST_DONE)) break;
 #else
-        if (warp_idle) break;
+        if (__all_sync(0xffffffffu, state == ST_DONE)) break;
 #endif
 
         // ---- phase B: one trace for every lane that has a ray ----------------------------------------
         TraceAcc<T> acc;
         acc.mode = (state == ST_RADIANCE) ? MODE_RADIANCE : (state == ST_SHADOW) ? MODE_SHADOW : (state == ST_CONTAINER) ? MODE_CONTAINER : MODE_IDLE;
-        if (resume_pos >= 0) acc.mode = MODE_IDLE;  // the parked primary hit stands in for the trace
         acc.best_t = (state == ST_SHADOW) ? shadow_distance : Real<T>::max();
         acc.dir_sq = fma(ray.d.z, ray.d.z, fma(ray.d.y, ray.d.y, ray.d.x * ray.d.x));
         acc.best_orig = 0x7fffffff;
@@ -979,25 +936,11 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
         V3<T> colour = mk<T>(T(0), T(0), T(0));
         T n1 = T(1), n2 = T(1);  // Material::DEFAULT_REFRACTIVE_INDEX, material.rs:24
 
-        bool park = false;  // postpone this pixel (heavy pixels first)
-        if (state == ST_RADIANCE && resume_pos >= 0) {
-            acc.best_pos = resume_pos;  // a parked primary hit
-            acc.best_t = resume_t;
-            resume_pos = -1;
-        }
-        const bool ring_has_room = ring != nullptr && ring_count + 32u <= defer_cap;  // warp-uniform
         if (state == ST_RADIANCE) {
             // World::internal_color_at, world.rs:70-86
             if (acc.best_pos < 0) {
-                primary = false;
                 returning = true;  // World::DEFAULT_COLOR
-            } else if (primary && ring_has_room &&
-                       sv.material((uint32_t)sv.shape_meta((uint32_t)acc.best_pos).y)[MAT_TRANSPARENCY] == T(0)) {
-                park = true;  // an ordinary pixel met during the first sweep: shade it later
-                primary = false;
-                state = ST_FETCH;
             } else {
-                primary = false;
                 ++c_nodes;
                 hit_pos = acc.best_pos;
                 t_hit = acc.best_t;
@@ -1200,22 +1143,6 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
             else
                 colour = (f.surface + f.a) + f.refr_o;
             returning = true;
-        }
-
-        // park the primary hits of this round in the warp's ring (warp-aggregated append)
-        if (ring != nullptr) {
-            const unsigned parking = __ballot_sync(0xffffffffu, park);
-            if (parking) {
-                if (park) {
-                    Deferred<T> d;
-                    d.t = acc.best_t;
-                    d.pos = acc.best_pos;
-                    d.slot = cur_slot;
-                    ring[ring_count + __popc(parking & ((1u << lane) - 1u))] = d;
-                }
-                ring_count += __popc(parking);
-                __syncwarp();  // entries are read back by other lanes of this warp
-            }
         }
     }
 

@@ -52,7 +52,6 @@ struct PackedScene {
     std::vector<int> ints;
     rt::SceneLayout layout;
     bool has_cyl_cone_tri = false;
-    bool has_transparent = false;
 };
 
 int validate_scene(const rtgpu_scene* s) {
@@ -394,7 +393,6 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
         }
     }
     for (uint32_t m = 0; m < M; ++m) {
-        if (s->mat_params[(size_t)m * RTGPU_MAT_PARAM_COUNT + RTGPU_MAT_TRANSPARENCY] != 0.0) out->has_transparent = true;
         double* d = R + lay.mat_off + (size_t)m * rt::MAT_REALS;
         memcpy(d, s->mat_color + (size_t)m * 3, 3 * sizeof(double));
         memcpy(d + 3, s->mat_params + (size_t)m * RTGPU_MAT_PARAM_COUNT, RTGPU_MAT_PARAM_COUNT * sizeof(double));
@@ -499,9 +497,6 @@ struct rtgpu_context {
     size_t smem_optin = 0;
     bool has_cyl_cone_tri = false;  // selects the kernel instantiated with those shape types
     size_t cap_reals = 0, cap_ints = 0;
-    bool has_transparent = false;  // some material has transparency != 0: the scene has "heavy" pixels
-    void* d_defer = nullptr;       // per-warp rings of parked primary hits
-    size_t defer_bytes = 0;
     bool zero_copy = false;  // the last host render wrote straight into the caller's pinned buffers
 };
 
@@ -528,29 +523,8 @@ int launch_kernel_impl(rtgpu_context* ctx, const T* d_reals, const rt::CameraPar
     uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)blocks_per_sm;
     if (grid > blocks_needed) grid = blocks_needed;
     if (grid < 1) grid = 1;
-    // "heavy pixels first" (rt_kernel.cuh): one ring of parked primary hits per warp.  Only scenes with a
-    // transparent material have heavy pixels; RTGPU_DEFER=0 switches the mechanism off (A/B).
-    rt::Deferred<T>* d_defer = nullptr;
-    uint32_t defer_cap = 0;
-    const char* defer_env = getenv("RTGPU_DEFER");
-    if (ctx->has_transparent && !(defer_env && defer_env[0] == '0')) {
-        const uint64_t n_warps = grid * (RT_BLOCK_THREADS / 32);
-        uint64_t cap = 2 * ((slots + n_warps - 1) / n_warps) + 96;
-        cap = (cap + 31) & ~31ull;
-        const size_t bytes = (size_t)(n_warps * cap) * sizeof(rt::Deferred<T>);
-        if (bytes > ctx->defer_bytes) {
-            if (ctx->d_defer) cudaFree(ctx->d_defer);
-            ctx->d_defer = nullptr;
-            ctx->defer_bytes = 0;
-            CUDA_TRY(cudaMalloc(&ctx->d_defer, bytes));
-            ctx->defer_bytes = bytes;
-        }
-        d_defer = reinterpret_cast<rt::Deferred<T>*>(ctx->d_defer);
-        defer_cap = (uint32_t)cap;
-    }
     CUDA_TRY(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), stream));
-    kernel<<<(unsigned)grid, RT_BLOCK_THREADS, smem, stream>>>(d_reals, ctx->d_ints, lay, cam, d_out, d_out8, d_counters, ctx->d_work,
-                                                                  d_defer, defer_cap);
+    kernel<<<(unsigned)grid, RT_BLOCK_THREADS, smem, stream>>>(d_reals, ctx->d_ints, lay, cam, d_out, d_out8, d_counters, ctx->d_work);
     CUDA_TRY(cudaGetLastError());
     return RTGPU_OK;
 }
@@ -651,7 +625,6 @@ int upload_scene(rtgpu_context* ctx, const PackedScene& packed) {
     ctx->d_reals32 = nullptr;
     ctx->layout = lay;
     ctx->has_cyl_cone_tri = packed.has_cyl_cone_tri;
-    ctx->has_transparent = packed.has_transparent;
     // repeated frames of similar scenes reuse the allocations (cudaFree / cudaMalloc synchronise the device)
     const size_t need_reals = std::max<size_t>(16, (size_t)lay.n_reals * sizeof(double));
     const size_t need_ints = std::max<size_t>(16, (size_t)lay.n_ints * sizeof(int));
@@ -706,7 +679,6 @@ void context_release(rtgpu_context* ctx) {
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_out8) cudaFree(ctx->d_out8);
-    if (ctx->d_defer) cudaFree(ctx->d_defer);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -723,7 +695,6 @@ int ensure_out_buffers(rtgpu_context* ctx, size_t rgb_bytes, size_t rgb8_bytes) 
     }
     if (rgb8_bytes > ctx->d_out8_bytes) {
         if (ctx->d_out8) cudaFree(ctx->d_out8);
-    if (ctx->d_defer) cudaFree(ctx->d_defer);
         ctx->d_out8 = nullptr;
         ctx->d_out8_bytes = 0;
         CUDA_TRY(cudaMalloc(&ctx->d_out8, rgb8_bytes));
