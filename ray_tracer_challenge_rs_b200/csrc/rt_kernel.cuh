@@ -754,6 +754,10 @@ enum : int { ST_FETCH = 0, ST_RADIANCE = 1, ST_CONTAINER = 2, ST_SHADOW = 3, ST_
 #define RT_MIN_BLOCKS_PER_SM 4
 #endif
 
+#ifndef RT_TMA_STAGE
+#define RT_TMA_STAGE 1  // scene tables -> shared memory by cp.async.bulk + mbarrier (0: plain loads)
+#endif
+
 #ifndef RT_UNIFIED_LOOP
 #define RT_UNIFIED_LOOP 1
 #endif
@@ -787,9 +791,41 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
     if (layout.in_shared) {
         T* s_reals = reinterpret_cast<T*>(smem_raw);
         int* s_ints = reinterpret_cast<int*>(smem_raw + (((size_t)layout.n_reals * sizeof(T) + 15) & ~size_t(15)));
+#if RT_TMA_STAGE
+        // Stage both scene blobs with the TMA unit: two bulk asynchronous copies (cp.async.bulk, SASS UBLKCP)
+        // issued by one thread, completion counted in bytes on an mbarrier that every thread then waits on.
+        // The packer pads both blobs to multiples of 16 bytes, and cudaMalloc / the shared window are aligned.
+        __shared__ __align__(8) unsigned long long stage_bar;
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&stage_bar);
+        const uint32_t bytes_reals = layout.n_reals * (uint32_t)sizeof(T), bytes_ints = layout.n_ints * (uint32_t)sizeof(int);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes_reals + bytes_ints) : "memory");
+            if (bytes_reals)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 (uint32_t)__cvta_generic_to_shared(s_reals)),
+                             "l"(g_reals), "r"(bytes_reals), "r"(bar)
+                             : "memory");
+            if (bytes_ints)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 (uint32_t)__cvta_generic_to_shared(s_ints)),
+                             "l"(g_ints), "r"(bytes_ints), "r"(bar)
+                             : "memory");
+        }
+        {
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+        }
+#else
         for (uint32_t i = threadIdx.x; i < layout.n_reals; i += blockDim.x) s_reals[i] = g_reals[i];
         for (uint32_t i = threadIdx.x; i < layout.n_ints; i += blockDim.x) s_ints[i] = g_ints[i];
         __syncthreads();
+#endif
         sv.reals = s_reals;
         sv.ints = s_ints;
     } else {

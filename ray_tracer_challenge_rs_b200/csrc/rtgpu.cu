@@ -346,7 +346,7 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     lay.cull_off = (lay.light_off + L * rt::LIGHT_REALS + 1u) & ~1u;  // 16-byte aligned records
     lay.bvh_off = lay.cull_off + S * rt::CULL_REALS;
     lay.n_reals = lay.bvh_off + lay.n_bvh_nodes * rt::BVH_REALS;
-    lay.n_reals = (lay.n_reals + 1u) & ~1u;
+    lay.n_reals = (lay.n_reals + 3u) & ~3u;  // 16-byte multiple in f32 too (bulk copies into shared memory)
     lay.mat_meta_off = S * rt::SHAPE_INTS;
     lay.pat_meta_off = lay.mat_meta_off + M * rt::MAT_INTS;
     lay.bvh_meta_off = (lay.pat_meta_off + Q * rt::PAT_INTS + 1u) & ~1u;
