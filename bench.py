@@ -245,7 +245,7 @@ def run_b200(args):
     K, W = args.steps, max(args.warmup, 0)
     elem = 8 if args.precision == "f64" else 4
     tdtype = torch.float64 if args.precision == "f64" else torch.float32
-    rows = (16, rank, world) if world > 1 else None
+    rows = (4, rank, world) if world > 1 else None  # one tile row per band: finest balance across ranks
 
     renderer = Renderer(flat, device=local_rank)
     my_rows = renderer.rows_count(camera, rows)
@@ -347,7 +347,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": device_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic: the reference's cover scene (committed flattened fixture), camera resized to 1920x1080",
-            "config": workload_config(args, flat, {"parallelism": f"row bands of 16 rows, interleaved over {world} GPU(s); no collective in the data path"}),
+            "config": workload_config(args, flat, {"parallelism": f"row bands of 4 rows, interleaved over {world} GPU(s); no collective in the data path"}),
             "e2e": e2e, "gpu_launches": 2 * K * world, "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_summary,
             "rays_per_frame": rays, "ms_per_frame": device_ms / K, "wall_ms_per_step_incl_flush": (t_wall1 - t_wall0) * 1e3 / K,
             "counters": stats,

@@ -246,3 +246,15 @@ def test_showcase_yaml_scene(bvh_min, monkeypatch):
     monkeypatch.setenv("RTGPU_BVH_MIN", bvh_min)
     world, camera = load_scene_description(os.path.join(os.path.dirname(os.path.abspath(__file__)), "scenes", "showcase.yaml"))
     compare_with_oracle(world.flatten(), camera, label=f"showcase:bvh_min={bvh_min}")
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_world_fuzz(seed, monkeypatch):
+    """Seeded random worlds (tests/random_worlds.py): all shape and pattern kinds under rotations, shears and
+    anisotropic scales, glass / mirror / matte materials, duplicates — flat traversal and, every other seed, BVH."""
+    from random_worlds import random_world
+
+    if seed % 2:
+        monkeypatch.setenv("RTGPU_BVH_MIN", "1")
+    world, cam = random_world(1000 + seed)
+    compare_with_oracle(world.flatten(), cam, label=f"fuzz{seed}")
