@@ -165,6 +165,14 @@ typedef struct rtgpu_opts {
 } rtgpu_opts;
 
 #define RTGPU_FLAG_NONE 0u
+/* Kernel family (both produce the same pixels).  Default: RTGPU_WAVEFRONT=0/1 in the environment, else the
+ * library's built-in choice.
+ *   PERSISTENT : one launch; every lane walks one pixel's recursion tree with an explicit stack.
+ *   WAVEFRONT  : one launch per recursion level over queues of rays (+ a bottom-up combine per level).
+ *                rtgpu_context_render_device then blocks until the frame is complete (it has to verify that
+ *                its ray / node buffers were large enough, and renders again with larger ones if not). */
+#define RTGPU_FLAG_WAVEFRONT 1u
+#define RTGPU_FLAG_PERSISTENT 2u
 
 /* Work counters (integers, identical between devices, shardings and the CPU oracle) and timings. */
 typedef struct rtgpu_stats {

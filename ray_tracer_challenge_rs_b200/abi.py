@@ -31,6 +31,9 @@ MAT_PARAM_COUNT = 7
 # rtgpu_precision
 PRECISION_F64 = 0
 PRECISION_F32 = 1
+# rtgpu_opts.flags
+FLAG_WAVEFRONT = 1
+FLAG_PERSISTENT = 2
 
 _pd = C.POINTER(C.c_double)
 _pu8 = C.POINTER(C.c_uint8)

@@ -1,0 +1,470 @@
+// rt_wavefront.cuh — the render pass as a wavefront over recursion LEVELS (the second kernel family).
+//
+// The persistent kernel of rt_kernel.cuh evaluates a pixel's whole recursion tree (world.rs:70-157) on one
+// lane, one ray at a time: a camera ray that meets glass grows a tree of ~100 dependent rays, and the launch
+// cannot end before the slowest such chain does (profiles/r1_notes.md: a 1080p frame stops scaling at ~4
+// GPUs).  Here the unit of work is a NODE of some pixel's tree, and all nodes of one depth are processed by
+// one launch:
+//
+//   level d kernel : one thread per radiance ray of depth d.  Trace it (nearest hit); on a hit create the
+//                    node: prepare_computations (intersection.rs:21-75, with the container re-trace when
+//                    the material is transparent), the light loop with its shadow rays (world.rs:43-53),
+//                    then append the reflected / refracted rays (world.rs:114-157) to the queue of level
+//                    d+1.  A miss leaves the parent's slot black (World::DEFAULT_COLOR).
+//   combine kernel : levels from the deepest up.  A node's colour is `surface + reflected + refracted`
+//                    (Schlick-weighted when reflective and transparent, world.rs:59-66) and is written, scaled
+//                    by the parent's reflectiveness / transparency (world.rs:127,156), into the parent's
+//                    slot — or into the pixel for level 0.
+//
+// Every arithmetic operation of a node is the one the persistent kernel (and the reference) performs, in
+// the same order; only WHEN a node is evaluated changes.  The critical path is max_depth+1 launches
+// instead of the longest ray chain, lanes of a warp are always in the same phase, and sibling rays stay
+// together in the queues.  Queues and node records live in HBM: 64 B per queued ray, 112 B per node (f64).
+#pragma once
+
+#include "rt_kernel.cuh"
+
+namespace rt {
+
+template <typename T>
+struct WfRay {
+    T ox, oy, oz, dx, dy, dz;
+    int parent;  // node that spawned the ray
+    int slot;    // 0: its reflected colour, 1: its refracted colour
+};
+
+template <typename T>
+struct WfNode {
+    int parent;       // parent node, or -1 for a level-0 node
+    int slot;         // slot in the parent (0 reflected, 1 refracted); level 0: unused
+    unsigned pixel;   // level 0: output index of the pixel
+    int flags;        // FR_SCHLICK
+    T k_reflect, k_transparent, reflectance;
+    T surface[3];
+    T reflected[3];   // already scaled by k_reflect (world.rs:127); black until a child reports
+    T refracted[3];   // already scaled by k_transparent (world.rs:156)
+};
+
+// Device-side bookkeeping of one frame.
+struct WfCounts {
+    unsigned n_rays[16 + 2];   // rays queued for level d (level 0 = pixels, generated on the fly)
+    unsigned node_end[16 + 2]; // nodes created by levels 0..d end at node_end[d] (node_end[-1] = 0 implied)
+    unsigned n_nodes;          // nodes allocated so far
+    unsigned work;             // chunk cursor of the running launch
+    unsigned overflow;         // a queue or the node array was too small: the frame must be re-rendered
+};
+
+#ifndef RT_WF_THREADS
+#define RT_WF_THREADS 128
+#endif
+#ifndef RT_WF_MIN_BLOCKS
+#define RT_WF_MIN_BLOCKS 4
+#endif
+
+template <typename T>
+RT_DEV void wf_store_pixel(T* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8, size_t out_index, V3<T> colour) {
+    if (out_rgb) {
+        out_rgb[out_index * 3 + 0] = colour.x;
+        out_rgb[out_index * 3 + 1] = colour.y;
+        out_rgb[out_index * 3 + 2] = colour.z;
+    }
+    if (out_rgb8) {  // Canvas::to_png_file, canvas.rs:117-123
+        const T ch[3] = {colour.x, colour.y, colour.z};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            T v = ch[k];
+            v = (v < T(0)) ? T(0) : v;
+            v = (v > T(1)) ? T(1) : v;
+            v = round(v * T(255));
+            out_rgb8[out_index * 3 + k] = (v != v) ? (uint8_t)0 : (uint8_t)v;
+        }
+    }
+}
+
+template <typename T>
+RT_DEV void wf_reset_acc(TraceAcc<T>& acc, int mode, const Ray<T>& ray, T best_t) {
+    acc.mode = mode;
+    acc.best_t = best_t;
+    acc.dir_sq = fma(ray.d.z, ray.d.z, fma(ray.d.y, ray.d.y, ray.d.x * ray.d.x));
+    acc.best_orig = 0x7fffffff;
+    acc.best_pos = -1;
+    acc.c.t_hit = T(0);
+    acc.c.hit_class = -1;
+    acc.c.hit_class_inside = false;
+    acc.c.all_pos = acc.c.excl_pos = -1;
+    acc.c.all_t = acc.c.excl_t = T(0);
+    acc.c.all_orig = acc.c.excl_orig = 0;
+}
+
+template <typename T, bool FULL, bool BVH>
+RT_DEV void wf_trace(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
+#if RT_UNIFIED_LOOP
+    if (acc.mode != MODE_IDLE) trace_unified<T, FULL>(sv, ray, acc);
+#else
+    if (acc.mode != MODE_IDLE) trace<T, FULL>(sv, ray, acc);
+#endif
+    if (BVH) trace_bvh<T, FULL>(sv, ray, acc);  // warp votes inside: every lane takes part
+}
+
+template <typename T, bool FULL, bool BVH>
+__global__ void __launch_bounds__(RT_WF_THREADS, RT_WF_MIN_BLOCKS)
+wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, SceneLayout layout, CameraParams<T> cam, int level,
+                const WfRay<T>* __restrict__ rays_in, WfRay<T>* __restrict__ rays_out, unsigned cap_rays, WfNode<T>* __restrict__ nodes,
+                unsigned cap_nodes, WfCounts* __restrict__ counts, T* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8,
+                unsigned long long* __restrict__ counters) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SceneView<T> sv;
+    sv.L = layout;
+    if (layout.in_shared) {
+        T* s_reals = reinterpret_cast<T*>(smem_raw);
+        int* s_ints = reinterpret_cast<int*>(smem_raw + (((size_t)layout.n_reals * sizeof(T) + 15) & ~size_t(15)));
+        // cp.async.bulk + mbarrier staging, as in render_kernel
+        __shared__ __align__(8) unsigned long long stage_bar;
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&stage_bar);
+        const uint32_t bytes_reals = layout.n_reals * (uint32_t)sizeof(T), bytes_ints = layout.n_ints * (uint32_t)sizeof(int);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes_reals + bytes_ints) : "memory");
+            if (bytes_reals)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 (uint32_t)__cvta_generic_to_shared(s_reals)),
+                             "l"(g_reals), "r"(bytes_reals), "r"(bar)
+                             : "memory");
+            if (bytes_ints)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 (uint32_t)__cvta_generic_to_shared(s_ints)),
+                             "l"(g_ints), "r"(bytes_ints), "r"(bar)
+                             : "memory");
+        }
+        {
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+        }
+        sv.reals = s_reals;
+        sv.ints = s_ints;
+    } else {
+        sv.reals = g_reals;
+        sv.ints = g_ints;
+    }
+
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t tiles_x = (cam.hsize + TILE_W - 1) / TILE_W;
+    const uint32_t tiles_y = (cam.n_rows + TILE_H - 1) / TILE_H;
+    const unsigned n_items = level == 0 ? tiles_x * tiles_y * (TILE_W * TILE_H) : min(counts->n_rays[level], cap_rays);
+    const int n_lights = (int)layout.n_lights;
+    const int remaining = (int)cam.max_depth - level;
+    unsigned int c_primary = 0, c_shadow = 0, c_reflect = 0, c_refract = 0, c_nodes = 0;
+
+    for (;;) {
+        // one warp = 32 consecutive work items (one 8x4 tile of pixels, or 32 neighbouring queue entries)
+        unsigned first = 0;
+        if (lane == 0) first = atomicAdd(&counts->work, 32u);
+        first = __shfl_sync(0xffffffffu, first, 0);
+        if (first >= n_items) break;
+        const unsigned item = first + lane;
+
+        // ---- the radiance ray of this work item -------------------------------------------------
+        bool active = item < n_items;
+        Ray<T> ray;
+        ray.o = mk<T>(T(0), T(0), T(0));
+        ray.d = mk<T>(T(0), T(0), T(1));
+        int parent = -1, slot = 0;
+        size_t out_index = 0;
+        if (level == 0) {
+            if (active) {
+                const uint32_t tile = item / (TILE_W * TILE_H), in = item % (TILE_W * TILE_H);
+                const uint32_t x = (tile % tiles_x) * TILE_W + in % TILE_W;
+                const uint32_t k = (tile / tiles_x) * TILE_H + in / TILE_W;
+                active = x < cam.hsize && k < cam.n_rows;
+                if (active) {
+                    const uint32_t y = ((k / cam.band_rows) * cam.shard_count + cam.shard_index) * cam.band_rows + k % cam.band_rows;
+                    // Camera::ray_for_pixel, camera.rs:52-68
+                    T offset_x = (T(x) + T(0.5)) * cam.pixel_size;
+                    T offset_y = (T(y) + T(0.5)) * cam.pixel_size;
+                    T world_x = cam.half_width - offset_x;
+                    T world_y = cam.half_height - offset_y;
+                    V3<T> pixel = mat_point(cam.inv, mk<T>(world_x, world_y, T(-1)));
+                    V3<T> origin = ld3(cam.origin);
+                    ray.o = origin;
+                    ray.d = normalized(pixel - origin);
+                    out_index = (size_t)(cam.out_full_frame ? y : k) * cam.hsize + x;
+                    ++c_primary;
+                }
+            }
+        } else if (active) {
+            const WfRay<T> r = rays_in[item];
+            ray.o = mk<T>(r.ox, r.oy, r.oz);
+            ray.d = mk<T>(r.dx, r.dy, r.dz);
+            parent = r.parent;
+            slot = r.slot;
+        }
+
+        // ---- World::internal_color_at (world.rs:70-86): nearest hit --------------------------------
+        TraceAcc<T> acc;
+        wf_reset_acc(acc, active ? MODE_RADIANCE : MODE_IDLE, ray, Real<T>::max());
+        wf_trace<T, FULL, BVH>(sv, ray, acc);
+        const bool hit = active && acc.best_pos >= 0;
+        if (active && !hit && level == 0) wf_store_pixel(out_rgb, out_rgb8, out_index, mk<T>(T(0), T(0), T(0)));  // World::DEFAULT_COLOR
+        // (a deeper miss leaves the parent's slot black, which is what the parent was initialised with)
+
+        // ---- node allocation (warp-aggregated) -----------------------------------------------------
+        const unsigned hits = __ballot_sync(0xffffffffu, hit);
+        unsigned node_base = 0;
+        if (lane == 0 && hits) node_base = atomicAdd(&counts->n_nodes, (unsigned)__popc(hits));
+        node_base = __shfl_sync(0xffffffffu, node_base, 0);
+        const unsigned node_index = node_base + __popc(hits & ((1u << lane) - 1u));
+        bool alive = hit;
+        if (hit && node_index >= cap_nodes) {
+            counts->overflow = 1u;
+            alive = false;
+        }
+
+        // ---- Intersection::prepare_computations (intersection.rs:21-31, computed_hit.rs:33-34) --------
+        V3<T> over = ray.o, under = ray.o, normal = ray.d, eye = ray.d, reflect_dir = ray.d;
+        int hit_pos = 0, hit_material = 0;
+        T t_hit = T(0);
+        bool need_containers = false;
+        if (alive) {
+            ++c_nodes;
+            hit_pos = acc.best_pos;
+            t_hit = acc.best_t;
+            const T* g = sv.shape((uint32_t)hit_pos);
+            const int4 meta = sv.shape_meta((uint32_t)hit_pos);
+            hit_material = meta.y;
+            V3<T> point = ray.o + ray.d * t_hit;
+            V3<T> local_point = mat_point(g, point);  // shape.rs:22-27
+            V3<T> local_normal = local_normal_at(sv, (uint32_t)hit_pos, (meta.z >> FLAG_TYPE_SHIFT) & 7, g, local_point);
+            normal = normalized(mat_transposed_vector(g, local_normal));
+            eye = neg(ray.d);
+            if (dot(normal, eye) < T(0)) normal = neg(normal);
+            reflect_dir = reflect(ray.d, normal);  // intersection.rs:31
+            over = point + (normal * Real<T>::offset_eps());
+            under = point - (normal * Real<T>::offset_eps());
+            // n1 / n2 only feed refracted_color and Schlick, both irrelevant without iterations left
+            need_containers = sv.material((uint32_t)hit_material)[MAT_TRANSPARENCY] != T(0) && remaining > 0;
+        }
+
+        // ---- refraction containers (intersection.rs:33-62): second query along the same ray -----------
+        T n1 = T(1), n2 = T(1);  // Material::DEFAULT_REFRACTIVE_INDEX
+        if (__any_sync(0xffffffffu, need_containers)) {
+            wf_reset_acc(acc, need_containers ? MODE_CONTAINER : MODE_IDLE, ray, Real<T>::max());
+            acc.c.t_hit = t_hit;
+            acc.c.hit_class = need_containers ? sv.shape_meta((uint32_t)hit_pos).w : -1;
+            wf_trace<T, FULL, BVH>(sv, ray, acc);
+            if (need_containers) {
+                n1 = (acc.c.all_pos >= 0) ? sv.material((uint32_t)sv.shape_meta((uint32_t)acc.c.all_pos).y)[MAT_REFRACTIVE_INDEX] : T(1);
+                if (acc.c.hit_class_inside)
+                    n2 = (acc.c.excl_pos >= 0) ? sv.material((uint32_t)sv.shape_meta((uint32_t)acc.c.excl_pos).y)[MAT_REFRACTIVE_INDEX] : T(1);
+                else
+                    n2 = sv.material((uint32_t)hit_material)[MAT_REFRACTIVE_INDEX];
+            }
+        }
+
+        // ---- children to spawn, Schlick, base colour ----------------------------------------------------
+        int flags = 0;
+        T reflectance = T(0), k_reflect = T(0), k_transparent = T(0);
+        V3<T> refr_d = ray.d, base = ray.d;
+        if (alive) {
+            const T* m = sv.material((uint32_t)hit_material);
+            k_reflect = m[MAT_REFLECTIVENESS];
+            k_transparent = m[MAT_TRANSPARENCY];
+            if (remaining > 0 && m[MAT_REFLECTIVENESS] != T(0)) flags |= FR_REFLECT;  // world.rs:120
+            const T cos_i = dot(eye, normal);
+            if (remaining > 0 && m[MAT_TRANSPARENCY] != T(0)) {  // world.rs:136-154
+                T n_ratio = n1 / n2;
+                T sin2_t = sq(n_ratio) * (T(1) - sq(cos_i));
+                if (!(sin2_t > T(1))) {
+                    T cos_t = sqrt(T(1) - sin2_t);
+                    refr_d = (normal * fma(n_ratio, cos_i, -cos_t)) - (eye * n_ratio);
+                    flags |= FR_REFRACT;
+                }
+            }
+            if (m[MAT_REFLECTIVENESS] > T(0) && m[MAT_TRANSPARENCY] > T(0)) {  // world.rs:59
+                flags |= FR_SCHLICK;
+                T c = cos_i;  // ComputedHit::schlicks_approximation, computed_hit.rs:50-68
+                bool total = false;
+                if (n1 > n2) {
+                    T ratio = n1 / n2;
+                    T sin2_t = sq(ratio) * (T(1) - sq(c));
+                    if (sin2_t > T(1)) total = true;
+                    else c = sqrt(T(1) - sin2_t);
+                }
+                if (total) {
+                    reflectance = T(1);
+                } else {
+                    T r0 = sq((n1 - n2) / (n1 + n2));
+                    T x = T(1) - c;
+                    T x5 = x * ((x * x) * (x * x));  // powi(5)
+                    reflectance = fma(T(1) - r0, x5, r0);
+                }
+            }
+            // Material::resolve_color, material.rs:75-80
+            const int pat = sv.material_pattern((uint32_t)hit_material);
+            if (pat >= 0) {
+                V3<T> object_point = mat_point(sv.shape((uint32_t)hit_pos), over);  // pattern.rs:10-14
+                V3<T> pattern_point = mat_point(sv.pattern((uint32_t)pat) + 6, object_point);
+                base = pattern_color_at(sv, pat, pattern_point);
+            } else {
+                base = ld3(m);
+            }
+        }
+
+        // ---- the light loop (world.rs:43-53): one shadow query + Material::lighting per light --------
+        V3<T> surface = mk<T>(T(0), T(0), T(0));
+        for (int light = 0; light < n_lights; ++light) {
+            const T* lt = sv.light((uint32_t)light);
+            Ray<T> sray;
+            sray.o = over;
+            sray.d = ray.d;
+            T distance = T(0);
+            if (alive) {  // World::is_in_shadow, world.rs:98-112
+                Normalized<T> nl = normalize_full(ld3(lt) - over);
+                sray.d = nl.v;
+                distance = nl.magnitude;
+                ++c_shadow;
+            }
+            wf_reset_acc(acc, alive ? MODE_SHADOW : MODE_IDLE, sray, distance);
+            wf_trace<T, FULL, BVH>(sv, sray, acc);
+            if (alive) {  // Material::lighting, material.rs:53-114, at over_point (material.rs:116-130)
+                const T* m = sv.material((uint32_t)hit_material);
+                V3<T> intensity = ld3(lt + 3);
+                V3<T> effective = hadamard(base, intensity);
+                V3<T> ambient = effective * m[MAT_AMBIENT];
+                V3<T> lit = ambient;
+                if (!(acc.best_pos >= 0)) {
+                    V3<T> light_dir = normalized(ld3(lt) - over);
+                    T ldn = dot(light_dir, normal);
+                    if (!(ldn < T(0))) {
+                        V3<T> diffuse = (effective * m[MAT_DIFFUSE]) * ldn;
+                        V3<T> refl = reflect(neg(light_dir), normal);
+                        T rde = dot(refl, eye);
+                        if (rde <= T(0) || m[MAT_SPECULAR] == T(0)) {  // see render_kernel: an exact zero term
+                            lit = ambient + diffuse;
+                        } else {
+                            T factor = pow(rde, m[MAT_SHININESS]);
+                            V3<T> specular = (intensity * m[MAT_SPECULAR]) * factor;
+                            lit = (ambient + diffuse) + specular;
+                        }
+                    }
+                }
+                surface = surface + lit;  // fold(Color::BLACK, Color::add)
+            }
+        }
+
+        // ---- the node record ---------------------------------------------------------------------------
+        if (alive) {
+            WfNode<T> nd;
+            nd.parent = parent;
+            nd.slot = slot;
+            nd.pixel = (unsigned)out_index;
+            nd.flags = flags & FR_SCHLICK;
+            nd.k_reflect = k_reflect;
+            nd.k_transparent = k_transparent;
+            nd.reflectance = reflectance;
+            nd.surface[0] = surface.x; nd.surface[1] = surface.y; nd.surface[2] = surface.z;
+            nd.reflected[0] = nd.reflected[1] = nd.reflected[2] = T(0);  // world.rs:121
+            nd.refracted[0] = nd.refracted[1] = nd.refracted[2] = T(0);  // world.rs:137,146
+            nodes[node_index] = nd;
+        }
+
+        // ---- children (world.rs:114-157) appended to the next level's queue, siblings adjacent ----------
+        const int n_children = alive ? (((flags & FR_REFLECT) ? 1 : 0) + ((flags & FR_REFRACT) ? 1 : 0)) : 0;
+        int prefix = n_children;  // inclusive warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, prefix, o);
+            if ((int)lane >= o) prefix += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, prefix, 31);
+        if (total) {
+            unsigned qbase = 0;
+            if (lane == 0) qbase = atomicAdd(&counts->n_rays[level + 1], (unsigned)total);
+            qbase = __shfl_sync(0xffffffffu, qbase, 0);
+            unsigned q = qbase + (unsigned)(prefix - n_children);
+            if (flags & FR_REFLECT && alive) {
+                if (q < cap_rays) {
+                    WfRay<T> r;
+                    r.ox = over.x; r.oy = over.y; r.oz = over.z;
+                    r.dx = reflect_dir.x; r.dy = reflect_dir.y; r.dz = reflect_dir.z;
+                    r.parent = (int)node_index;
+                    r.slot = 0;
+                    rays_out[q] = r;
+                    ++c_reflect;
+                } else {
+                    counts->overflow = 1u;
+                }
+                ++q;
+            }
+            if (flags & FR_REFRACT && alive) {
+                if (q < cap_rays) {
+                    WfRay<T> r;
+                    r.ox = under.x; r.oy = under.y; r.oz = under.z;
+                    r.dx = refr_d.x; r.dy = refr_d.y; r.dz = refr_d.z;
+                    r.parent = (int)node_index;
+                    r.slot = 1;
+                    rays_out[q] = r;
+                    ++c_refract;
+                } else {
+                    counts->overflow = 1u;
+                }
+            }
+        }
+    }
+
+    if (counters) {
+        unsigned int vals[5] = {c_primary, c_shadow, c_reflect, c_refract, c_nodes};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            unsigned int v = vals[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && v) atomicAdd(&counters[k], (unsigned long long)v);
+        }
+        unsigned int px = c_primary;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) px += __shfl_xor_sync(0xffffffffu, px, o);
+        if (lane == 0 && px) atomicAdd(&counters[COUNTER_PIXELS], (unsigned long long)px);
+    }
+}
+
+// Called between levels: remember where this level's nodes end, reset the chunk cursor.
+__global__ void wf_advance_kernel(WfCounts* counts, int level) {
+    counts->node_end[level] = counts->n_nodes;
+    counts->work = 0u;
+}
+
+// World::shade_hit's tail (world.rs:59-66) for the nodes of one level, deepest level first.
+template <typename T>
+__global__ void wf_combine_kernel(WfNode<T>* __restrict__ nodes, const WfCounts* __restrict__ counts, int level, unsigned cap_nodes,
+                                  T* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8) {
+    const unsigned begin = level == 0 ? 0u : min(counts->node_end[level - 1], cap_nodes);
+    const unsigned end = min(counts->node_end[level], cap_nodes);
+    for (unsigned i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
+        const WfNode<T>& n = nodes[i];
+        const V3<T> surface = mk<T>(n.surface[0], n.surface[1], n.surface[2]);
+        const V3<T> reflected = mk<T>(n.reflected[0], n.reflected[1], n.reflected[2]);
+        const V3<T> refracted = mk<T>(n.refracted[0], n.refracted[1], n.refracted[2]);
+        V3<T> colour;
+        if (n.flags & FR_SCHLICK) colour = (surface + (reflected * n.reflectance)) + (refracted * (T(1) - n.reflectance));
+        else colour = (surface + reflected) + refracted;
+        if (n.parent < 0) {
+            wf_store_pixel(out_rgb, out_rgb8, (size_t)n.pixel, colour);  // Camera::render_parallel, camera.rs:108
+        } else {
+            WfNode<T>& p = nodes[n.parent];
+            if (n.slot == 0) {
+                const V3<T> c = colour * p.k_reflect;  // world.rs:127
+                p.reflected[0] = c.x; p.reflected[1] = c.y; p.reflected[2] = c.z;
+            } else {
+                const V3<T> c = colour * p.k_transparent;  // world.rs:156
+                p.refracted[0] = c.x; p.refracted[1] = c.y; p.refracted[2] = c.z;
+            }
+        }
+    }
+}
+
+}  // namespace rt

@@ -20,6 +20,7 @@
 #include "../../include/rtgpu.h"
 #include "rt_bvh.h"
 #include "rt_kernel.cuh"
+#include "rt_wavefront.cuh"
 #include "rt_scene.h"
 
 namespace {
@@ -498,6 +499,14 @@ struct rtgpu_context {
     bool has_cyl_cone_tri = false;  // selects the kernel instantiated with those shape types
     size_t cap_reals = 0, cap_ints = 0;
     bool zero_copy = false;  // the last host render wrote straight into the caller's pinned buffers
+    // wavefront path (rt_wavefront.cuh): two ray queues, the node array and the frame's bookkeeping
+    void* d_wf_rays[2] = {nullptr, nullptr};
+    void* d_wf_nodes = nullptr;
+    rt::WfCounts* d_wf_counts = nullptr;
+    unsigned long long* d_wf_priv = nullptr;  // the frame's own work counters, committed to the caller's once it is complete
+    size_t wf_cap_rays = 0, wf_cap_nodes = 0;  // in elements
+    size_t wf_bytes_rays = 0, wf_bytes_nodes = 0;
+    bool wf_used = false;  // the last launch took the wavefront path (overflow must be checked after it)
 };
 
 namespace {
@@ -527,6 +536,128 @@ int launch_kernel_impl(rtgpu_context* ctx, const T* d_reals, const rt::CameraPar
     kernel<<<(unsigned)grid, RT_BLOCK_THREADS, smem, stream>>>(d_reals, ctx->d_ints, lay, cam, d_out, d_out8, d_counters, ctx->d_work);
     CUDA_TRY(cudaGetLastError());
     return RTGPU_OK;
+}
+
+// ---- wavefront path ------------------------------------------------------------------------------
+
+#ifndef RTGPU_DEFAULT_WAVEFRONT
+#define RTGPU_DEFAULT_WAVEFRONT 0
+#endif
+
+__global__ void wf_commit_counters_kernel(const unsigned long long* priv, unsigned long long* user) {
+    if (threadIdx.x < rt::NUM_COUNTERS && priv[threadIdx.x]) atomicAdd(&user[threadIdx.x], priv[threadIdx.x]);
+}
+
+bool wavefront_requested(const rtgpu_opts* opts) {
+    if (opts && (opts->flags & RTGPU_FLAG_PERSISTENT)) return false;
+    if (opts && (opts->flags & RTGPU_FLAG_WAVEFRONT)) return true;
+    const char* e = getenv("RTGPU_WAVEFRONT");
+    if (e && *e) return e[0] != '0';
+    return RTGPU_DEFAULT_WAVEFRONT != 0;
+}
+
+template <typename T>
+int wavefront_reserve(rtgpu_context* ctx, uint64_t pixels, double growth) {
+    // first guess: 3 queued rays and 5 nodes per pixel; after an overflow the caller asks for more
+    size_t want_rays = std::max<size_t>((size_t)(3.0 * growth * (double)pixels), 1u << 16);
+    size_t want_nodes = std::max<size_t>((size_t)(5.0 * growth * (double)pixels), 1u << 16);
+    want_rays = std::min<size_t>(want_rays, 0xFFFFFF00u);
+    want_nodes = std::min<size_t>(want_nodes, 0x7FFFFF00u);
+    const size_t bytes_rays = want_rays * sizeof(rt::WfRay<T>), bytes_nodes = want_nodes * sizeof(rt::WfNode<T>);
+    if (bytes_rays > ctx->wf_bytes_rays) {
+        for (int k = 0; k < 2; ++k) {
+            if (ctx->d_wf_rays[k]) cudaFree(ctx->d_wf_rays[k]);
+            ctx->d_wf_rays[k] = nullptr;
+        }
+        ctx->wf_bytes_rays = 0;
+        for (int k = 0; k < 2; ++k) CUDA_TRY(cudaMalloc(&ctx->d_wf_rays[k], bytes_rays));
+        ctx->wf_bytes_rays = bytes_rays;
+    }
+    if (bytes_nodes > ctx->wf_bytes_nodes) {
+        if (ctx->d_wf_nodes) cudaFree(ctx->d_wf_nodes);
+        ctx->d_wf_nodes = nullptr;
+        ctx->wf_bytes_nodes = 0;
+        CUDA_TRY(cudaMalloc(&ctx->d_wf_nodes, bytes_nodes));
+        ctx->wf_bytes_nodes = bytes_nodes;
+    }
+    ctx->wf_cap_rays = ctx->wf_bytes_rays / sizeof(rt::WfRay<T>);
+    ctx->wf_cap_nodes = ctx->wf_bytes_nodes / sizeof(rt::WfNode<T>);
+    if (!ctx->d_wf_counts) CUDA_TRY(cudaMalloc(&ctx->d_wf_counts, sizeof(rt::WfCounts)));
+    if (!ctx->d_wf_priv) CUDA_TRY(cudaMalloc(&ctx->d_wf_priv, rt::NUM_COUNTERS * sizeof(unsigned long long)));
+    return RTGPU_OK;
+}
+
+template <typename T, bool FULL, bool BVH>
+int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::CameraParams<T>& cam, T* d_out, uint8_t* d_out8,
+                          unsigned long long* d_counters, cudaStream_t stream) {
+    auto level_kernel = rt::wf_level_kernel<T, FULL, BVH>;
+    rt::SceneLayout lay = ctx->layout;
+    size_t smem = (((size_t)lay.n_reals * sizeof(T) + 15) & ~size_t(15)) + (size_t)lay.n_ints * sizeof(int);
+    const size_t smem_cap = std::min<size_t>(ctx->smem_optin, 64 * 1024);
+    lay.in_shared = smem <= smem_cap ? 1u : 0u;
+    if (!lay.in_shared) smem = 0;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks_per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, level_kernel, RT_WF_THREADS, smem));
+    if (blocks_per_sm < 1) return fail(RTGPU_ERR_CUDA, "wavefront kernel does not fit on an SM (smem %zu B)", smem);
+    const uint64_t pixels = (uint64_t)cam.hsize * cam.n_rows;
+    if (ctx->wf_cap_rays == 0 || ctx->wf_bytes_rays / sizeof(rt::WfRay<T>) < 3 * pixels / 2) {
+        int st = wavefront_reserve<T>(ctx, pixels, 1.0);
+        if (st != RTGPU_OK) return st;
+    }
+    ctx->wf_cap_rays = ctx->wf_bytes_rays / sizeof(rt::WfRay<T>);
+    ctx->wf_cap_nodes = ctx->wf_bytes_nodes / sizeof(rt::WfNode<T>);
+    const unsigned grid = (unsigned)(ctx->sm_count * blocks_per_sm);
+    const int levels = (int)cam.max_depth + 1;
+    CUDA_TRY(cudaMemsetAsync(ctx->d_wf_counts, 0, sizeof(rt::WfCounts), stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_wf_priv, 0, rt::NUM_COUNTERS * sizeof(unsigned long long), stream));
+    (void)d_counters;
+    rt::WfNode<T>* nodes = reinterpret_cast<rt::WfNode<T>*>(ctx->d_wf_nodes);
+    for (int level = 0; level < levels; ++level) {
+        const rt::WfRay<T>* in = reinterpret_cast<const rt::WfRay<T>*>(ctx->d_wf_rays[level & 1]);
+        rt::WfRay<T>* out = reinterpret_cast<rt::WfRay<T>*>(ctx->d_wf_rays[(level + 1) & 1]);
+        level_kernel<<<grid, RT_WF_THREADS, smem, stream>>>(d_reals, ctx->d_ints, lay, cam, level, in, out, (unsigned)ctx->wf_cap_rays, nodes,
+                                                            (unsigned)ctx->wf_cap_nodes, ctx->d_wf_counts, d_out, d_out8, ctx->d_wf_priv);
+        rt::wf_advance_kernel<<<1, 1, 0, stream>>>(ctx->d_wf_counts, level);
+    }
+    for (int level = levels - 1; level >= 0; --level)
+        rt::wf_combine_kernel<T><<<ctx->sm_count * 4, 256, 0, stream>>>(nodes, ctx->d_wf_counts, level, (unsigned)ctx->wf_cap_nodes, d_out, d_out8);
+    CUDA_TRY(cudaGetLastError());
+    ctx->wf_used = true;
+    return RTGPU_OK;
+}
+
+template <typename T>
+int launch_wavefront(rtgpu_context* ctx, const T* d_reals, const rt::CameraParams<T>& cam, T* d_out, uint8_t* d_out8,
+                     unsigned long long* d_counters, cudaStream_t stream) {
+    const bool full = ctx->has_cyl_cone_tri;
+    const bool bvh = ctx->layout.n_bvh_nodes > 0;
+    if (bvh) {
+        if (full) return launch_wavefront_impl<T, true, true>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+        return launch_wavefront_impl<T, false, true>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    }
+    if (full) return launch_wavefront_impl<T, true, false>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    return launch_wavefront_impl<T, false, false>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+}
+
+// After a wavefront launch has completed on `stream`: did a queue or the node array overflow?
+// Returns 1 (and enlarges the buffers) when the frame has to be rendered again, 0 when it is complete.
+template <typename T>
+int wavefront_check(rtgpu_context* ctx, uint64_t pixels, cudaStream_t stream) {
+    if (!ctx->wf_used) return 0;
+    ctx->wf_used = false;
+    rt::WfCounts h;
+    CUDA_TRY(cudaMemcpyAsync(&h, ctx->d_wf_counts, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (!h.overflow) return 0;
+    // what the frame actually asked for, with headroom
+    unsigned max_rays = 0;
+    for (int d = 0; d < 18; ++d) max_rays = std::max(max_rays, h.n_rays[d]);
+    const double g_rays = (double)max_rays / (3.0 * (double)pixels), g_nodes = (double)h.n_nodes / (5.0 * (double)pixels);
+    const double growth = std::max(1.25 * std::max(g_rays, g_nodes), 2.0 * (double)ctx->wf_cap_rays / (3.0 * (double)pixels));
+    int st = wavefront_reserve<T>(ctx, pixels, growth);
+    if (st != RTGPU_OK) return st;
+    return 1;
 }
 
 template <typename T, int MAX_FRAMES>
@@ -589,9 +720,33 @@ int check_opts(const rtgpu_opts* opts, uint32_t* precision, uint32_t* max_depth)
     return RTGPU_OK;
 }
 
+// One frame through the wavefront family.  blocking: wait, verify the buffers were large enough, render again
+// with larger ones otherwise.  Non-blocking callers must run wavefront_check themselves after the stream drains.
+template <typename T>
+int render_wavefront(rtgpu_context* ctx, const T* d_reals, const rt::CameraParams<T>& cam, T* d_out, uint8_t* d_out8,
+                     unsigned long long* counters, cudaStream_t stream, bool blocking) {
+    const uint64_t pixels = (uint64_t)cam.hsize * cam.n_rows;
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        int st = launch_wavefront<T>(ctx, d_reals, cam, d_out, d_out8, counters, stream);
+        if (st != RTGPU_OK) return st;
+        if (!blocking) {
+            if (counters) wf_commit_counters_kernel<<<1, 32, 0, stream>>>(ctx->d_wf_priv, counters);
+            return RTGPU_OK;
+        }
+        st = wavefront_check<T>(ctx, pixels, stream);
+        if (st < 0) return st;
+        if (st == 0) {
+            if (counters) wf_commit_counters_kernel<<<1, 32, 0, stream>>>(ctx->d_wf_priv, counters);
+            CUDA_TRY(cudaGetLastError());
+            return RTGPU_OK;
+        }
+    }
+    return fail(RTGPU_ERR_OUT_OF_MEMORY, "wavefront buffers kept overflowing");
+}
+
 int render_device_impl(rtgpu_context* ctx, const rtgpu_camera* camera, const rtgpu_opts* opts, const rtgpu_rows* rows,
                        void* d_out_rgb, uint8_t* d_out_rgb8, uint64_t* d_counters, cudaStream_t stream, uint32_t* out_n_rows,
-                       bool full_frame_out = false) {
+                       bool full_frame_out = false, bool wavefront_blocking = true) {
     if (!ctx || !camera) return fail(RTGPU_ERR_INVALID_ARGUMENT, "context or camera is NULL");
     if (!d_out_rgb && !d_out_rgb8) return fail(RTGPU_ERR_INVALID_ARGUMENT, "both output pointers are NULL");
     uint32_t precision, max_depth;
@@ -608,6 +763,7 @@ int render_device_impl(rtgpu_context* ctx, const rtgpu_camera* camera, const rtg
     if (precision == RTGPU_PRECISION_F64) {
         rt::CameraParams<double> cam;
         fill_camera(camera, sel, n_rows, max_depth, full_frame_out, &cam);
+        if (wavefront_requested(opts)) return render_wavefront<double>(ctx, ctx->d_reals64, cam, (double*)d_out_rgb, d_out_rgb8, counters, stream, wavefront_blocking);
         if (max_depth <= 7) return launch_kernel<double, 8>(ctx, ctx->d_reals64, cam, (double*)d_out_rgb, d_out_rgb8, counters, stream);
         return launch_kernel<double, 16>(ctx, ctx->d_reals64, cam, (double*)d_out_rgb, d_out_rgb8, counters, stream);
     }
@@ -615,6 +771,7 @@ int render_device_impl(rtgpu_context* ctx, const rtgpu_camera* camera, const rtg
     if (st != RTGPU_OK) return st;
     rt::CameraParams<float> cam;
     fill_camera(camera, sel, n_rows, max_depth, full_frame_out, &cam);
+    if (wavefront_requested(opts)) return render_wavefront<float>(ctx, ctx->d_reals32, cam, (float*)d_out_rgb, d_out_rgb8, counters, stream, wavefront_blocking);
     if (max_depth <= 7) return launch_kernel<float, 8>(ctx, ctx->d_reals32, cam, (float*)d_out_rgb, d_out_rgb8, counters, stream);
     return launch_kernel<float, 16>(ctx, ctx->d_reals32, cam, (float*)d_out_rgb, d_out_rgb8, counters, stream);
 }
@@ -679,6 +836,11 @@ void context_release(rtgpu_context* ctx) {
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_out8) cudaFree(ctx->d_out8);
+    for (int k = 0; k < 2; ++k)
+        if (ctx->d_wf_rays[k]) cudaFree(ctx->d_wf_rays[k]);
+    if (ctx->d_wf_nodes) cudaFree(ctx->d_wf_nodes);
+    if (ctx->d_wf_counts) cudaFree(ctx->d_wf_counts);
+    if (ctx->d_wf_priv) cudaFree(ctx->d_wf_priv);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -695,6 +857,11 @@ int ensure_out_buffers(rtgpu_context* ctx, size_t rgb_bytes, size_t rgb8_bytes) 
     }
     if (rgb8_bytes > ctx->d_out8_bytes) {
         if (ctx->d_out8) cudaFree(ctx->d_out8);
+    for (int k = 0; k < 2; ++k)
+        if (ctx->d_wf_rays[k]) cudaFree(ctx->d_wf_rays[k]);
+    if (ctx->d_wf_nodes) cudaFree(ctx->d_wf_nodes);
+    if (ctx->d_wf_counts) cudaFree(ctx->d_wf_counts);
+    if (ctx->d_wf_priv) cudaFree(ctx->d_wf_priv);
         ctx->d_out8 = nullptr;
         ctx->d_out8_bytes = 0;
         CUDA_TRY(cudaMalloc(&ctx->d_out8, rgb8_bytes));
@@ -745,13 +912,13 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
     if (ctx->zero_copy) {
         st = render_device_impl(ctx, camera, opts, rows, map_rgb, (uint8_t*)map_rgb8, reinterpret_cast<uint64_t*>(ctx->d_counters),
-                                ctx->stream, nullptr, /*full_frame_out=*/true);
+                                ctx->stream, nullptr, /*full_frame_out=*/true, /*wavefront_blocking=*/false);
         if (st != RTGPU_OK) return st;
         CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
         return RTGPU_OK;
     }
     st = render_device_impl(ctx, camera, opts, rows, out_rgb ? ctx->d_out : nullptr, out_rgb8 ? ctx->d_out8 : nullptr,
-                            reinterpret_cast<uint64_t*>(ctx->d_counters), ctx->stream, nullptr);
+                            reinterpret_cast<uint64_t*>(ctx->d_counters), ctx->stream, nullptr, false, /*wavefront_blocking=*/false);
     if (st != RTGPU_OK) return st;
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     // compact band b (rows [b*band_rows, ...)) of this shard -> image rows of band (b*shard_count + shard_index)
@@ -768,9 +935,24 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
     return RTGPU_OK;
 }
 
-int finish_host_render(rtgpu_context* ctx, rtgpu_stats* stats) {
+int finish_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rtgpu_opts* opts, const rtgpu_rows* rows, void* out_rgb,
+                       uint8_t* out_rgb8, rtgpu_stats* stats) {
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    // wavefront family: if a queue or the node array was too small the buffers have been enlarged: render again
+    for (int attempt = 0; ctx->wf_used && attempt < 8; ++attempt) {
+        RowSel sel;
+        int st = normalise_rows(rows, camera->vsize, &sel);
+        if (st != RTGPU_OK) return st;
+        const uint64_t pixels = (uint64_t)camera->hsize * count_rows(sel, camera->vsize);
+        const bool f64 = !opts || opts->precision == RTGPU_PRECISION_F64;
+        st = f64 ? wavefront_check<double>(ctx, pixels, ctx->stream) : wavefront_check<float>(ctx, pixels, ctx->stream);
+        if (st < 0) return st;
+        if (st == 0) break;
+        st = enqueue_host_render(ctx, camera, opts, rows, out_rgb, out_rgb8);
+        if (st != RTGPU_OK) return st;
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
     if (stats) {
         unsigned long long c[rt::NUM_COUNTERS];
         CUDA_TRY(cudaMemcpy(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
@@ -940,7 +1122,7 @@ int rtgpu_context_render(rtgpu_context* context, const rtgpu_camera* camera, con
     if (stats) memset(stats, 0, sizeof(*stats));
     int st = enqueue_host_render(context, camera, opts, rows, out_rgb, out_rgb8);
     if (st != RTGPU_OK) return st;
-    st = finish_host_render(context, stats);
+    st = finish_host_render(context, camera, opts, rows, out_rgb, out_rgb8, stats);
     if (st != RTGPU_OK) return st;
     if (stats) stats->total_ms = wall_ms() - t0;
     return RTGPU_OK;
@@ -994,7 +1176,11 @@ int rtgpu_render(const rtgpu_scene* scene, const rtgpu_camera* camera, const rtg
         if (st != RTGPU_OK) return st;
     }
     for (int g = 0; g < n_gpus; ++g) {
-        st = finish_host_render(cache[g], stats);
+        rtgpu_rows rows;
+        rows.band_rows = n_gpus == 1 ? 0u : band_rows;
+        rows.shard_index = (uint32_t)g;
+        rows.shard_count = (uint32_t)n_gpus;
+        st = finish_host_render(cache[g], camera, opts, &rows, out_rgb, out_rgb8, stats);
         if (st != RTGPU_OK) return st;
     }
     if (stats) stats->total_ms = wall_ms() - t0;

@@ -21,9 +21,12 @@ def _flat(scene: SceneLike) -> FlatScene:
     return scene if isinstance(scene, FlatScene) else flatten_world(scene)
 
 
-def _opts(precision: str = "f64", max_depth: int = World.MAX_REFLECTION_ITERATIONS, n_gpus: int = 1, band_rows: int = 16) -> abi.RtgpuOpts:
+def _opts(precision: str = "f64", max_depth: int = World.MAX_REFLECTION_ITERATIONS, n_gpus: int = 1, band_rows: int = 16,
+          family: Optional[str] = None) -> abi.RtgpuOpts:
+    """family: None (library default / RTGPU_WAVEFRONT), "wavefront" or "persistent" (include/rtgpu.h RTGPU_FLAG_*)."""
     prec = {"f64": abi.PRECISION_F64, "f32": abi.PRECISION_F32}[precision]
-    return abi.RtgpuOpts(prec, int(max_depth), int(n_gpus), int(band_rows), 0)
+    flags = {None: 0, "wavefront": abi.FLAG_WAVEFRONT, "persistent": abi.FLAG_PERSISTENT}[family]
+    return abi.RtgpuOpts(prec, int(max_depth), int(n_gpus), int(band_rows), flags)
 
 
 def device_count() -> int:
@@ -40,6 +43,7 @@ def render_gpu(
     want_rgb: bool = True,
     want_rgb8: bool = True,
     return_stats: bool = False,
+    family: Optional[str] = None,
 ):
     """One-shot render through ``rtgpu_render`` (the call a ``RenderingMode::Gpu`` arm makes).
 
@@ -54,7 +58,7 @@ def render_gpu(
     rgb = np.zeros((n, 3), dtype) if want_rgb else None
     rgb8 = np.zeros((n, 3), np.uint8) if want_rgb8 else None
     stats = abi.RtgpuStats()
-    opts = _opts(precision, max_depth, n_gpus, band_rows)
+    opts = _opts(precision, max_depth, n_gpus, band_rows, family)
     st = lib.rtgpu_render(
         C.byref(cscene),
         C.byref(ccam),
@@ -113,6 +117,7 @@ class Renderer:
         out_rgb8: Optional[np.ndarray] = None,
         want_rgb: bool = True,
         want_rgb8: bool = True,
+        family: Optional[str] = None,
     ):
         """Host buffers in, host buffers out (``rtgpu_context_render``): full-frame arrays; only the
         rows that ``rows = (band_rows, shard_index, shard_count)`` selects are written."""
@@ -123,7 +128,7 @@ class Renderer:
         if out_rgb8 is None and want_rgb8:
             out_rgb8 = np.zeros((n, 3), np.uint8)
         ccam = camera_to_c(camera)
-        opts = _opts(precision, max_depth)
+        opts = _opts(precision, max_depth, family=family)
         r = abi.RtgpuRows(*(rows or (0, 0, 1)))
         stats = abi.RtgpuStats()
         st = self._lib.rtgpu_context_render(
@@ -148,11 +153,12 @@ class Renderer:
         precision: str = "f64",
         max_depth: int = World.MAX_REFLECTION_ITERATIONS,
         rows: Optional[Tuple[int, int, int]] = None,
+        family: Optional[str] = None,
     ) -> None:
         """Asynchronous launch on device pointers and a caller-owned stream
         (``rtgpu_context_render_device``); outputs are compact over the selected rows."""
         ccam = camera_to_c(camera)
-        opts = _opts(precision, max_depth)
+        opts = _opts(precision, max_depth, family=family)
         r = abi.RtgpuRows(*(rows or (0, 0, 1)))
         st = self._lib.rtgpu_context_render_device(
             self._ctx, C.byref(ccam), C.byref(opts), C.byref(r), d_out_rgb or None, d_out_rgb8 or None, d_counters or None, stream or None

@@ -31,8 +31,8 @@ COUNTERS = ("rays_primary", "rays_shadow", "rays_reflect", "rays_refract", "hit_
 F64_RTOL = 1e-12  # pow() ulp noise only; anything structural is orders of magnitude larger
 
 
-def compare_with_oracle(flat, camera, max_depth=6, label=""):
-    canvas, gstats = render_gpu(camera, flat, max_depth=max_depth, return_stats=True)
+def compare_with_oracle(flat, camera, max_depth=6, label="", family=None):
+    canvas, gstats = render_gpu(camera, flat, max_depth=max_depth, return_stats=True, family=family)
     rgb, rgb8, ostats = Oracle(flat).render(camera, max_depth=max_depth, threads=0)
     g8 = canvas.to_rgb8().reshape(-1, 3)
     w = camera.horizontal_size
@@ -258,3 +258,71 @@ def test_random_world_fuzz(seed, monkeypatch):
         monkeypatch.setenv("RTGPU_BVH_MIN", "1")
     world, cam = random_world(1000 + seed)
     compare_with_oracle(world.flatten(), cam, label=f"fuzz{seed}")
+
+
+# ---------------------------------------------------------------------------------------------
+# The wavefront kernel family (csrc/rt_wavefront.cuh): same pixels, one launch per recursion level.
+
+
+@pytest.mark.parametrize("name", SHIPPED_SCENES)
+def test_wavefront_shipped_scene_small(name):
+    flat, camera = load_scene_fixture(name)
+    cam = camera.resized(384, 384 * camera.vertical_size // camera.horizontal_size)
+    compare_with_oracle(flat, cam, label=f"wavefront:{name}", family="wavefront")
+
+
+@pytest.mark.parametrize("name", sorted(SPECIAL_WORLDS))
+def test_wavefront_special_world(name):
+    world, camera = SPECIAL_WORLDS[name]()
+    compare_with_oracle(world.flatten(), camera, label=f"wavefront:{name}", family="wavefront")
+
+
+@pytest.mark.parametrize("max_depth", [0, 1, 3, 5, 7, 9])
+def test_wavefront_recursion_depths(max_depth):
+    flat, camera = load_scene_fixture("refraction")
+    compare_with_oracle(flat, camera.resized(96, 96), max_depth=max_depth, label=f"wavefront:refraction@{max_depth}", family="wavefront")
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_wavefront_random_world_fuzz(seed, monkeypatch):
+    from random_worlds import random_world
+
+    if seed % 2:
+        monkeypatch.setenv("RTGPU_BVH_MIN", "1")
+    world, cam = random_world(2000 + seed)
+    compare_with_oracle(world.flatten(), cam, label=f"wavefront:fuzz{seed}", family="wavefront")
+
+
+def test_wavefront_equals_persistent_bit_for_bit():
+    """Both families perform the same operations per node: identical f64 frames, identical counters — also on a
+    frame heavy enough (23 rays per pixel) to overflow the first-guess ray / node buffers and be re-rendered."""
+    for name, size in (("refraction", (512, 512)), ("cover", (640, 360)), ("cylinders", (480, 240))):
+        flat, camera = load_scene_fixture(name)
+        cam = camera.resized(*size)
+        a, sa = render_gpu(cam, flat, return_stats=True, family="persistent")
+        b, sb = render_gpu(cam, flat, return_stats=True, family="wavefront")
+        assert np.array_equal(a.pixels.view(np.uint64), b.pixels.view(np.uint64)), name
+        assert np.array_equal(a.to_rgb8(), b.to_rgb8()), name
+        assert {k: sa[k] for k in COUNTERS} == {k: sb[k] for k in COUNTERS}, name
+
+
+@pytest.mark.parametrize("name", ["cover", "refraction", "table"])
+def test_wavefront_native_size_matches_reference_png(name):
+    flat, camera = load_scene_fixture(name)
+    canvas = render_gpu(camera, flat, want_rgb=False, family="wavefront")
+    assert hashlib.sha256(np.ascontiguousarray(canvas.to_rgb8()).tobytes()).hexdigest() == INDEX[name]["sha256_rgb8"]
+
+
+def test_wavefront_shards_and_synthetic():
+    flat, camera = load_scene_fixture("reflect_refract")
+    cam = camera.resized(320, 214)
+    with Renderer(flat) as r:
+        whole, whole8, wstats = r.render(cam, family="wavefront")
+        rgb = np.full_like(whole, np.nan)
+        rgb8 = np.zeros_like(whole8)
+        for index in range(3):
+            r.render(cam, rows=(8, index, 3), out_rgb=rgb, out_rgb8=rgb8, family="wavefront")
+    assert np.array_equal(rgb.view(np.uint64), whole.view(np.uint64)) and np.array_equal(rgb8, whole8)
+    from ray_tracer_challenge_rs_b200.synthetic import synthetic_camera, synthetic_scene
+
+    compare_with_oracle(synthetic_scene(3000, extent=9.0), synthetic_camera(192, 108, distance=23.4), label="wavefront:synthetic3000", family="wavefront")
