@@ -609,6 +609,9 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
     ctx->wf_cap_nodes = ctx->wf_bytes_nodes / sizeof(rt::WfNode<T>);
     const unsigned grid = (unsigned)(ctx->sm_count * blocks_per_sm);
     const int levels = (int)cam.max_depth + 1;
+    if (!ctx->d_wf_counts || !ctx->d_wf_priv || !ctx->d_wf_nodes || !ctx->d_wf_rays[0] || !ctx->d_wf_rays[1])
+        return fail(RTGPU_ERR_CUDA, "wavefront buffers missing (counts %p priv %p nodes %p rays %p %p, cap %zu %zu)", (void*)ctx->d_wf_counts,
+                    (void*)ctx->d_wf_priv, ctx->d_wf_nodes, ctx->d_wf_rays[0], ctx->d_wf_rays[1], ctx->wf_cap_rays, ctx->wf_cap_nodes);
     CUDA_TRY(cudaMemsetAsync(ctx->d_wf_counts, 0, sizeof(rt::WfCounts), stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_wf_priv, 0, rt::NUM_COUNTERS * sizeof(unsigned long long), stream));
     (void)d_counters;
@@ -618,7 +621,9 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
         rt::WfRay<T>* out = reinterpret_cast<rt::WfRay<T>*>(ctx->d_wf_rays[(level + 1) & 1]);
         level_kernel<<<grid, RT_WF_THREADS, smem, stream>>>(d_reals, ctx->d_ints, lay, cam, level, in, out, (unsigned)ctx->wf_cap_rays, nodes,
                                                             (unsigned)ctx->wf_cap_nodes, ctx->d_wf_counts, d_out, d_out8, ctx->d_wf_priv);
+        CUDA_TRY(cudaGetLastError());
         rt::wf_advance_kernel<<<1, 1, 0, stream>>>(ctx->d_wf_counts, level);
+        CUDA_TRY(cudaGetLastError());
     }
     for (int level = levels - 1; level >= 0; --level)
         rt::wf_combine_kernel<T><<<ctx->sm_count * 4, 256, 0, stream>>>(nodes, ctx->d_wf_counts, level, (unsigned)ctx->wf_cap_nodes, d_out, d_out8);
@@ -857,11 +862,6 @@ int ensure_out_buffers(rtgpu_context* ctx, size_t rgb_bytes, size_t rgb8_bytes) 
     }
     if (rgb8_bytes > ctx->d_out8_bytes) {
         if (ctx->d_out8) cudaFree(ctx->d_out8);
-    for (int k = 0; k < 2; ++k)
-        if (ctx->d_wf_rays[k]) cudaFree(ctx->d_wf_rays[k]);
-    if (ctx->d_wf_nodes) cudaFree(ctx->d_wf_nodes);
-    if (ctx->d_wf_counts) cudaFree(ctx->d_wf_counts);
-    if (ctx->d_wf_priv) cudaFree(ctx->d_wf_priv);
         ctx->d_out8 = nullptr;
         ctx->d_out8_bytes = 0;
         CUDA_TRY(cudaMalloc(&ctx->d_out8, rgb8_bytes));
