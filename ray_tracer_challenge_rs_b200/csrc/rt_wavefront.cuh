@@ -6,11 +6,13 @@
 // GPUs).  Here the unit of work is a NODE of some pixel's tree, and all nodes of one depth are processed by
 // one launch:
 //
-//   level d kernel : one thread per radiance ray of depth d.  Trace it (nearest hit); on a hit create the
-//                    node: prepare_computations (intersection.rs:21-75, with the container re-trace when
-//                    the material is transparent), the light loop with its shadow rays (world.rs:43-53),
-//                    then append the reflected / refracted rays (world.rs:114-157) to the queue of level
-//                    d+1.  A miss leaves the parent's slot black (World::DEFAULT_COLOR).
+//   level d kernel : one thread per HIT of depth d (level 0: per pixel, the camera ray is traced first).
+//                    Create the node: prepare_computations (intersection.rs:21-75, with the container
+//                    re-trace when the material is transparent), the light loop with its shadow rays
+//                    (world.rs:43-53); then trace the reflected / refracted rays (world.rs:114-157) right
+//                    away and append only those that HIT something to the queue of level d+1 — a miss is
+//                    World::DEFAULT_COLOR, i.e. the black the parent's slot already holds.  So every queue
+//                    entry is a node-to-be and no lane of a deeper launch idles on a miss.
 //   combine kernel : levels from the deepest up.  A node's colour is `surface + reflected + refracted`
 //                    (Schlick-weighted when reflective and transparent, world.rs:59-66) and is written, scaled
 //                    by the parent's reflectiveness / transparency (world.rs:127,156), into the parent's
@@ -26,11 +28,15 @@
 
 namespace rt {
 
+// A queued hit: the radiance ray, where it hit, and whose child it is.
 template <typename T>
 struct WfRay {
     T ox, oy, oz, dx, dy, dz;
+    T t;         // hit distance (Intersections::hit, intersections.rs:13-18)
+    int pos;     // sorted position of the hit shape
     int parent;  // node that spawned the ray
     int slot;    // 0: its reflected colour, 1: its refracted colour
+    int pad;
 };
 
 template <typename T>
@@ -196,21 +202,30 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                     ++c_primary;
                 }
             }
-        } else if (active) {
-            const WfRay<T> r = rays_in[item];
-            ray.o = mk<T>(r.ox, r.oy, r.oz);
-            ray.d = mk<T>(r.dx, r.dy, r.dz);
-            parent = r.parent;
-            slot = r.slot;
         }
 
         // ---- World::internal_color_at (world.rs:70-86): nearest hit --------------------------------
         TraceAcc<T> acc;
-        wf_reset_acc(acc, active ? MODE_RADIANCE : MODE_IDLE, ray, Real<T>::max());
-        wf_trace<T, FULL, BVH>(sv, ray, acc);
-        const bool hit = active && acc.best_pos >= 0;
-        if (active && !hit && level == 0) wf_store_pixel(out_rgb, out_rgb8, out_index, mk<T>(T(0), T(0), T(0)));  // World::DEFAULT_COLOR
-        // (a deeper miss leaves the parent's slot black, which is what the parent was initialised with)
+        bool hit;
+        if (level == 0) {
+            wf_reset_acc(acc, active ? MODE_RADIANCE : MODE_IDLE, ray, Real<T>::max());
+            wf_trace<T, FULL, BVH>(sv, ray, acc);
+            hit = active && acc.best_pos >= 0;
+            if (active && !hit) wf_store_pixel(out_rgb, out_rgb8, out_index, mk<T>(T(0), T(0), T(0)));  // World::DEFAULT_COLOR
+        } else {
+            // the parent's launch already traced this ray and only queued it because it hit
+            wf_reset_acc(acc, MODE_IDLE, ray, Real<T>::max());
+            if (active) {
+                const WfRay<T> r = rays_in[item];
+                ray.o = mk<T>(r.ox, r.oy, r.oz);
+                ray.d = mk<T>(r.dx, r.dy, r.dz);
+                parent = r.parent;
+                slot = r.slot;
+                acc.best_pos = r.pos;
+                acc.best_t = r.t;
+            }
+            hit = active;
+        }
 
         // ---- node allocation (warp-aggregated) -----------------------------------------------------
         const unsigned hits = __ballot_sync(0xffffffffu, hit);
@@ -372,45 +387,41 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
             nodes[node_index] = nd;
         }
 
-        // ---- children (world.rs:114-157) appended to the next level's queue, siblings adjacent ----------
-        const int n_children = alive ? (((flags & FR_REFLECT) ? 1 : 0) + ((flags & FR_REFRACT) ? 1 : 0)) : 0;
-        int prefix = n_children;  // inclusive warp scan
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int v = __shfl_up_sync(0xffffffffu, prefix, o);
-            if ((int)lane >= o) prefix += v;
-        }
-        const int total = __shfl_sync(0xffffffffu, prefix, 31);
-        if (total) {
-            unsigned qbase = 0;
-            if (lane == 0) qbase = atomicAdd(&counts->n_rays[level + 1], (unsigned)total);
-            qbase = __shfl_sync(0xffffffffu, qbase, 0);
-            unsigned q = qbase + (unsigned)(prefix - n_children);
-            if (flags & FR_REFLECT && alive) {
-                if (q < cap_rays) {
-                    WfRay<T> r;
-                    r.ox = over.x; r.oy = over.y; r.oz = over.z;
-                    r.dx = reflect_dir.x; r.dy = reflect_dir.y; r.dz = reflect_dir.z;
-                    r.parent = (int)node_index;
-                    r.slot = 0;
-                    rays_out[q] = r;
-                    ++c_reflect;
-                } else {
-                    counts->overflow = 1u;
-                }
-                ++q;
+        // ---- children (world.rs:114-157): trace now, queue the ones that hit -------------------------------
+#pragma unroll 1
+        for (int child = 0; child < 2; ++child) {
+            const bool spawn = alive && (flags & (child == 0 ? FR_REFLECT : FR_REFRACT));
+            if (!__any_sync(0xffffffffu, spawn)) continue;
+            Ray<T> cray;
+            cray.o = child == 0 ? over : under;         // world.rs:124 / world.rs:152
+            cray.d = child == 0 ? reflect_dir : refr_d;
+            if (spawn) {
+                if (child == 0) ++c_reflect;
+                else ++c_refract;
             }
-            if (flags & FR_REFRACT && alive) {
-                if (q < cap_rays) {
-                    WfRay<T> r;
-                    r.ox = under.x; r.oy = under.y; r.oz = under.z;
-                    r.dx = refr_d.x; r.dy = refr_d.y; r.dz = refr_d.z;
-                    r.parent = (int)node_index;
-                    r.slot = 1;
-                    rays_out[q] = r;
-                    ++c_refract;
-                } else {
-                    counts->overflow = 1u;
+            wf_reset_acc(acc, spawn ? MODE_RADIANCE : MODE_IDLE, cray, Real<T>::max());
+            wf_trace<T, FULL, BVH>(sv, cray, acc);
+            const bool child_hit = spawn && acc.best_pos >= 0;
+            const unsigned queued = __ballot_sync(0xffffffffu, child_hit);
+            if (queued) {
+                unsigned qbase = 0;
+                if (lane == 0) qbase = atomicAdd(&counts->n_rays[level + 1], (unsigned)__popc(queued));
+                qbase = __shfl_sync(0xffffffffu, qbase, 0);
+                const unsigned q = qbase + __popc(queued & ((1u << lane) - 1u));
+                if (child_hit) {
+                    if (q < cap_rays) {
+                        WfRay<T> r;
+                        r.ox = cray.o.x; r.oy = cray.o.y; r.oz = cray.o.z;
+                        r.dx = cray.d.x; r.dy = cray.d.y; r.dz = cray.d.z;
+                        r.t = acc.best_t;
+                        r.pos = acc.best_pos;
+                        r.parent = (int)node_index;
+                        r.slot = child;
+                        r.pad = 0;
+                        rays_out[q] = r;
+                    } else {
+                        counts->overflow = 1u;
+                    }
                 }
             }
         }
