@@ -181,6 +181,8 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
         ray.d = mk<T>(T(0), T(0), T(1));
         int parent = -1, slot = 0;
         size_t out_index = 0;
+        int queued_pos = -1;
+        T queued_t = T(0);
         if (level == 0) {
             if (active) {
                 const uint32_t tile = item / (TILE_W * TILE_H), in = item % (TILE_W * TILE_H);
@@ -202,227 +204,232 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                     ++c_primary;
                 }
             }
-        }
-
-        // ---- World::internal_color_at (world.rs:70-86): nearest hit --------------------------------
-        TraceAcc<T> acc;
-        bool hit;
-        if (level == 0) {
-            wf_reset_acc(acc, active ? MODE_RADIANCE : MODE_IDLE, ray, Real<T>::max());
-            wf_trace<T, FULL, BVH>(sv, ray, acc);
-            hit = active && acc.best_pos >= 0;
-            if (active && !hit) wf_store_pixel(out_rgb, out_rgb8, out_index, mk<T>(T(0), T(0), T(0)));  // World::DEFAULT_COLOR
-        } else {
+        } else if (active) {
             // the parent's launch already traced this ray and only queued it because it hit
-            wf_reset_acc(acc, MODE_IDLE, ray, Real<T>::max());
-            if (active) {
-                const WfRay<T> r = rays_in[item];
-                ray.o = mk<T>(r.ox, r.oy, r.oz);
-                ray.d = mk<T>(r.dx, r.dy, r.dz);
-                parent = r.parent;
-                slot = r.slot;
-                acc.best_pos = r.pos;
-                acc.best_t = r.t;
-            }
-            hit = active;
+            const WfRay<T> r = rays_in[item];
+            ray.o = mk<T>(r.ox, r.oy, r.oz);
+            ray.d = mk<T>(r.dx, r.dy, r.dz);
+            parent = r.parent;
+            slot = r.slot;
+            queued_pos = r.pos;
+            queued_t = r.t;
         }
 
-        // ---- node allocation (warp-aggregated) -----------------------------------------------------
-        const unsigned hits = __ballot_sync(0xffffffffu, hit);
-        unsigned node_base = 0;
-        if (lane == 0 && hits) node_base = atomicAdd(&counts->n_nodes, (unsigned)__popc(hits));
-        node_base = __shfl_sync(0xffffffffu, node_base, 0);
-        const unsigned node_index = node_base + __popc(hits & ((1u << lane) - 1u));
-        bool alive = hit;
-        if (hit && node_index >= cap_nodes) {
-            counts->overflow = 1u;
-            alive = false;
-        }
-
-        // ---- Intersection::prepare_computations (intersection.rs:21-31, computed_hit.rs:33-34) --------
-        V3<T> over = ray.o, under = ray.o, normal = ray.d, eye = ray.d, reflect_dir = ray.d;
-        int hit_pos = 0, hit_material = 0;
-        T t_hit = T(0);
-        bool need_containers = false;
-        if (alive) {
-            ++c_nodes;
-            hit_pos = acc.best_pos;
-            t_hit = acc.best_t;
-            const T* g = sv.shape((uint32_t)hit_pos);
-            const int4 meta = sv.shape_meta((uint32_t)hit_pos);
-            hit_material = meta.y;
-            V3<T> point = ray.o + ray.d * t_hit;
-            V3<T> local_point = mat_point(g, point);  // shape.rs:22-27
-            V3<T> local_normal = local_normal_at(sv, (uint32_t)hit_pos, (meta.z >> FLAG_TYPE_SHIFT) & 7, g, local_point);
-            normal = normalized(mat_transposed_vector(g, local_normal));
-            eye = neg(ray.d);
-            if (dot(normal, eye) < T(0)) normal = neg(normal);
-            reflect_dir = reflect(ray.d, normal);  // intersection.rs:31
-            over = point + (normal * Real<T>::offset_eps());
-            under = point - (normal * Real<T>::offset_eps());
-            // n1 / n2 only feed refracted_color and Schlick, both irrelevant without iterations left
-            need_containers = sv.material((uint32_t)hit_material)[MAT_TRANSPARENCY] != T(0) && remaining > 0;
-        }
-
-        // ---- refraction containers (intersection.rs:33-62): second query along the same ray -----------
-        T n1 = T(1), n2 = T(1);  // Material::DEFAULT_REFRACTIVE_INDEX
-        if (__any_sync(0xffffffffu, need_containers)) {
-            wf_reset_acc(acc, need_containers ? MODE_CONTAINER : MODE_IDLE, ray, Real<T>::max());
-            acc.c.t_hit = t_hit;
-            acc.c.hit_class = need_containers ? sv.shape_meta((uint32_t)hit_pos).w : -1;
-            wf_trace<T, FULL, BVH>(sv, ray, acc);
-            if (need_containers) {
-                n1 = (acc.c.all_pos >= 0) ? sv.material((uint32_t)sv.shape_meta((uint32_t)acc.c.all_pos).y)[MAT_REFRACTIVE_INDEX] : T(1);
-                if (acc.c.hit_class_inside)
-                    n2 = (acc.c.excl_pos >= 0) ? sv.material((uint32_t)sv.shape_meta((uint32_t)acc.c.excl_pos).y)[MAT_REFRACTIVE_INDEX] : T(1);
-                else
-                    n2 = sv.material((uint32_t)hit_material)[MAT_REFRACTIVE_INDEX];
-            }
-        }
-
-        // ---- children to spawn, Schlick, base colour ----------------------------------------------------
-        int flags = 0;
-        T reflectance = T(0), k_reflect = T(0), k_transparent = T(0);
-        V3<T> refr_d = ray.d, base = ray.d;
-        if (alive) {
-            const T* m = sv.material((uint32_t)hit_material);
-            k_reflect = m[MAT_REFLECTIVENESS];
-            k_transparent = m[MAT_TRANSPARENCY];
-            if (remaining > 0 && m[MAT_REFLECTIVENESS] != T(0)) flags |= FR_REFLECT;  // world.rs:120
-            const T cos_i = dot(eye, normal);
-            if (remaining > 0 && m[MAT_TRANSPARENCY] != T(0)) {  // world.rs:136-154
-                T n_ratio = n1 / n2;
-                T sin2_t = sq(n_ratio) * (T(1) - sq(cos_i));
-                if (!(sin2_t > T(1))) {
-                    T cos_t = sqrt(T(1) - sin2_t);
-                    refr_d = (normal * fma(n_ratio, cos_i, -cos_t)) - (eye * n_ratio);
-                    flags |= FR_REFRACT;
-                }
-            }
-            if (m[MAT_REFLECTIVENESS] > T(0) && m[MAT_TRANSPARENCY] > T(0)) {  // world.rs:59
-                flags |= FR_SCHLICK;
-                T c = cos_i;  // ComputedHit::schlicks_approximation, computed_hit.rs:50-68
-                bool total = false;
-                if (n1 > n2) {
-                    T ratio = n1 / n2;
-                    T sin2_t = sq(ratio) * (T(1) - sq(c));
-                    if (sin2_t > T(1)) total = true;
-                    else c = sqrt(T(1) - sin2_t);
-                }
-                if (total) {
-                    reflectance = T(1);
-                } else {
-                    T r0 = sq((n1 - n2) / (n1 + n2));
-                    T x = T(1) - c;
-                    T x5 = x * ((x * x) * (x * x));  // powi(5)
-                    reflectance = fma(T(1) - r0, x5, r0);
-                }
-            }
-            // Material::resolve_color, material.rs:75-80
-            const int pat = sv.material_pattern((uint32_t)hit_material);
-            if (pat >= 0) {
-                V3<T> object_point = mat_point(sv.shape((uint32_t)hit_pos), over);  // pattern.rs:10-14
-                V3<T> pattern_point = mat_point(sv.pattern((uint32_t)pat) + 6, object_point);
-                base = pattern_color_at(sv, pat, pattern_point);
-            } else {
-                base = ld3(m);
-            }
-        }
-
-        // ---- the light loop (world.rs:43-53): one shadow query + Material::lighting per light --------
+        // per-node state, filled phase by phase
+        bool alive = false, need_containers = false;
+        unsigned node_index = 0;
+        V3<T> over = ray.o, under = ray.o, normal = ray.d, eye = ray.d, reflect_dir = ray.d, refr_d = ray.d, base = ray.d;
         V3<T> surface = mk<T>(T(0), T(0), T(0));
-        for (int light = 0; light < n_lights; ++light) {
-            const T* lt = sv.light((uint32_t)light);
-            Ray<T> sray;
-            sray.o = over;
-            sray.d = ray.d;
-            T distance = T(0);
-            if (alive) {  // World::is_in_shadow, world.rs:98-112
-                Normalized<T> nl = normalize_full(ld3(lt) - over);
-                sray.d = nl.v;
-                distance = nl.magnitude;
-                ++c_shadow;
+        int hit_pos = 0, hit_material = 0, flags = 0;
+        T t_hit = T(0), reflectance = T(0), k_reflect = T(0), k_transparent = T(0);
+
+        // Every query of a node goes through ONE copy of the intersection code: the phases below only differ in
+        // the ray they set up before it and in what they do with the answer after it.  (Five inlined copies
+        // made this kernel instruction-fetch bound: GPC instruction cache at 90 % of its request rate.)
+        //   phase 0        the radiance ray itself (level 0 only; deeper levels were traced by their parent)
+        //   phase 1        refraction containers, same ray (intersection.rs:33-62)
+        //   phase 2..1+L   one shadow ray per light (world.rs:43-53)
+        //   phase 2+L, 3+L the reflected / refracted child rays (world.rs:114-157)
+        const int n_phases = 4 + n_lights;
+#pragma unroll 1
+        for (int phase = 0; phase < n_phases; ++phase) {
+            Ray<T> tray = ray;
+            int mode = MODE_IDLE;
+            T seed = Real<T>::max();
+            const int light = phase - 2;
+            const int child = phase - 2 - n_lights;
+            bool spawn = false;
+            if (phase == 0) {
+                if (level == 0 && active) mode = MODE_RADIANCE;
+            } else if (phase == 1) {
+                if (need_containers) mode = MODE_CONTAINER;
+            } else if (child < 0) {
+                if (alive) {  // World::is_in_shadow, world.rs:98-112
+                    Normalized<T> nl = normalize_full(ld3(sv.light((uint32_t)light)) - over);
+                    tray.o = over;
+                    tray.d = nl.v;
+                    seed = nl.magnitude;
+                    mode = MODE_SHADOW;
+                    ++c_shadow;
+                }
+            } else {
+                spawn = alive && (flags & (child == 0 ? FR_REFLECT : FR_REFRACT));
+                if (spawn) {
+                    tray.o = child == 0 ? over : under;  // world.rs:124 / world.rs:152
+                    tray.d = child == 0 ? reflect_dir : refr_d;
+                    mode = MODE_RADIANCE;
+                    if (child == 0) ++c_reflect;
+                    else ++c_refract;
+                }
             }
-            wf_reset_acc(acc, alive ? MODE_SHADOW : MODE_IDLE, sray, distance);
-            wf_trace<T, FULL, BVH>(sv, sray, acc);
-            if (alive) {  // Material::lighting, material.rs:53-114, at over_point (material.rs:116-130)
-                const T* m = sv.material((uint32_t)hit_material);
-                V3<T> intensity = ld3(lt + 3);
-                V3<T> effective = hadamard(base, intensity);
-                V3<T> ambient = effective * m[MAT_AMBIENT];
-                V3<T> lit = ambient;
-                if (!(acc.best_pos >= 0)) {
-                    V3<T> light_dir = normalized(ld3(lt) - over);
-                    T ldn = dot(light_dir, normal);
-                    if (!(ldn < T(0))) {
-                        V3<T> diffuse = (effective * m[MAT_DIFFUSE]) * ldn;
-                        V3<T> refl = reflect(neg(light_dir), normal);
-                        T rde = dot(refl, eye);
-                        if (rde <= T(0) || m[MAT_SPECULAR] == T(0)) {  // see render_kernel: an exact zero term
-                            lit = ambient + diffuse;
+
+            TraceAcc<T> acc;
+            wf_reset_acc(acc, mode, tray, seed);
+            if (phase == 1 && need_containers) {
+                acc.c.t_hit = t_hit;
+                acc.c.hit_class = sv.shape_meta((uint32_t)hit_pos).w;
+            }
+            if (__any_sync(0xffffffffu, mode != MODE_IDLE)) wf_trace<T, FULL, BVH>(sv, tray, acc);
+
+            if (phase == 0) {
+                // ---- World::internal_color_at (world.rs:70-86): the hit, the node, prepare_computations ----
+                if (level != 0 && active) {
+                    acc.best_pos = queued_pos;
+                    acc.best_t = queued_t;
+                }
+                const bool hit = active && acc.best_pos >= 0;
+                if (level == 0 && active && !hit) wf_store_pixel(out_rgb, out_rgb8, out_index, mk<T>(T(0), T(0), T(0)));  // World::DEFAULT_COLOR
+                const unsigned hits = __ballot_sync(0xffffffffu, hit);
+                unsigned node_base = 0;
+                if (lane == 0 && hits) node_base = atomicAdd(&counts->n_nodes, (unsigned)__popc(hits));
+                node_base = __shfl_sync(0xffffffffu, node_base, 0);
+                node_index = node_base + __popc(hits & ((1u << lane) - 1u));
+                alive = hit;
+                if (hit && node_index >= cap_nodes) {
+                    counts->overflow = 1u;
+                    alive = false;
+                }
+                if (alive) {  // intersection.rs:21-31, computed_hit.rs:33-34
+                    ++c_nodes;
+                    hit_pos = acc.best_pos;
+                    t_hit = acc.best_t;
+                    const T* g = sv.shape((uint32_t)hit_pos);
+                    const int4 meta = sv.shape_meta((uint32_t)hit_pos);
+                    hit_material = meta.y;
+                    V3<T> point = ray.o + ray.d * t_hit;
+                    V3<T> local_point = mat_point(g, point);  // shape.rs:22-27
+                    V3<T> local_normal = local_normal_at(sv, (uint32_t)hit_pos, (meta.z >> FLAG_TYPE_SHIFT) & 7, g, local_point);
+                    normal = normalized(mat_transposed_vector(g, local_normal));
+                    eye = neg(ray.d);
+                    if (dot(normal, eye) < T(0)) normal = neg(normal);
+                    reflect_dir = reflect(ray.d, normal);  // intersection.rs:31
+                    over = point + (normal * Real<T>::offset_eps());
+                    under = point - (normal * Real<T>::offset_eps());
+                    // n1 / n2 only feed refracted_color and Schlick, both irrelevant without iterations left
+                    need_containers = sv.material((uint32_t)hit_material)[MAT_TRANSPARENCY] != T(0) && remaining > 0;
+                }
+            } else if (phase == 1) {
+                // ---- n1 / n2 (intersection.rs:39-58), children to spawn, Schlick, base colour --------------
+                T n1 = T(1), n2 = T(1);  // Material::DEFAULT_REFRACTIVE_INDEX
+                if (need_containers) {
+                    n1 = (acc.c.all_pos >= 0) ? sv.material((uint32_t)sv.shape_meta((uint32_t)acc.c.all_pos).y)[MAT_REFRACTIVE_INDEX] : T(1);
+                    if (acc.c.hit_class_inside)
+                        n2 = (acc.c.excl_pos >= 0) ? sv.material((uint32_t)sv.shape_meta((uint32_t)acc.c.excl_pos).y)[MAT_REFRACTIVE_INDEX] : T(1);
+                    else
+                        n2 = sv.material((uint32_t)hit_material)[MAT_REFRACTIVE_INDEX];
+                }
+                if (alive) {
+                    const T* m = sv.material((uint32_t)hit_material);
+                    k_reflect = m[MAT_REFLECTIVENESS];
+                    k_transparent = m[MAT_TRANSPARENCY];
+                    if (remaining > 0 && m[MAT_REFLECTIVENESS] != T(0)) flags |= FR_REFLECT;  // world.rs:120
+                    const T cos_i = dot(eye, normal);
+                    if (remaining > 0 && m[MAT_TRANSPARENCY] != T(0)) {  // world.rs:136-154
+                        T n_ratio = n1 / n2;
+                        T sin2_t = sq(n_ratio) * (T(1) - sq(cos_i));
+                        if (!(sin2_t > T(1))) {
+                            T cos_t = sqrt(T(1) - sin2_t);
+                            refr_d = (normal * fma(n_ratio, cos_i, -cos_t)) - (eye * n_ratio);
+                            flags |= FR_REFRACT;
+                        }
+                    }
+                    if (m[MAT_REFLECTIVENESS] > T(0) && m[MAT_TRANSPARENCY] > T(0)) {  // world.rs:59
+                        flags |= FR_SCHLICK;
+                        T c = cos_i;  // ComputedHit::schlicks_approximation, computed_hit.rs:50-68
+                        bool total = false;
+                        if (n1 > n2) {
+                            T ratio = n1 / n2;
+                            T sin2_t = sq(ratio) * (T(1) - sq(c));
+                            if (sin2_t > T(1)) total = true;
+                            else c = sqrt(T(1) - sin2_t);
+                        }
+                        if (total) {
+                            reflectance = T(1);
                         } else {
-                            T factor = pow(rde, m[MAT_SHININESS]);
-                            V3<T> specular = (intensity * m[MAT_SPECULAR]) * factor;
-                            lit = (ambient + diffuse) + specular;
+                            T r0 = sq((n1 - n2) / (n1 + n2));
+                            T x = T(1) - c;
+                            T x5 = x * ((x * x) * (x * x));  // powi(5)
+                            reflectance = fma(T(1) - r0, x5, r0);
+                        }
+                    }
+                    // Material::resolve_color, material.rs:75-80
+                    const int pat = sv.material_pattern((uint32_t)hit_material);
+                    if (pat >= 0) {
+                        V3<T> object_point = mat_point(sv.shape((uint32_t)hit_pos), over);  // pattern.rs:10-14
+                        V3<T> pattern_point = mat_point(sv.pattern((uint32_t)pat) + 6, object_point);
+                        base = pattern_color_at(sv, pat, pattern_point);
+                    } else {
+                        base = ld3(m);
+                    }
+                }
+            } else if (child < 0) {
+                // ---- Material::lighting, material.rs:53-114, at over_point (material.rs:116-130) ------------
+                if (alive) {
+                    const T* lt = sv.light((uint32_t)light);
+                    const T* m = sv.material((uint32_t)hit_material);
+                    V3<T> intensity = ld3(lt + 3);
+                    V3<T> effective = hadamard(base, intensity);
+                    V3<T> ambient = effective * m[MAT_AMBIENT];
+                    V3<T> lit = ambient;
+                    if (!(acc.best_pos >= 0)) {
+                        V3<T> light_dir = tray.d;  // normalized(light.position - over_point), the shadow ray's direction
+                        T ldn = dot(light_dir, normal);
+                        if (!(ldn < T(0))) {
+                            V3<T> diffuse = (effective * m[MAT_DIFFUSE]) * ldn;
+                            V3<T> refl = reflect(neg(light_dir), normal);
+                            T rde = dot(refl, eye);
+                            if (rde <= T(0) || m[MAT_SPECULAR] == T(0)) {  // see render_kernel: an exact zero term
+                                lit = ambient + diffuse;
+                            } else {
+                                T factor = pow(rde, m[MAT_SHININESS]);
+                                V3<T> specular = (intensity * m[MAT_SPECULAR]) * factor;
+                                lit = (ambient + diffuse) + specular;
+                            }
+                        }
+                    }
+                    surface = surface + lit;  // fold(Color::BLACK, Color::add)
+                }
+            } else {
+                // ---- a child that hit something becomes a work item of the next level -----------------------
+                const bool child_hit = spawn && acc.best_pos >= 0;
+                const unsigned queued = __ballot_sync(0xffffffffu, child_hit);
+                if (queued) {
+                    unsigned qbase = 0;
+                    if (lane == 0) qbase = atomicAdd(&counts->n_rays[level + 1], (unsigned)__popc(queued));
+                    qbase = __shfl_sync(0xffffffffu, qbase, 0);
+                    const unsigned q = qbase + __popc(queued & ((1u << lane) - 1u));
+                    if (child_hit) {
+                        if (q < cap_rays) {
+                            WfRay<T> r;
+                            r.ox = tray.o.x; r.oy = tray.o.y; r.oz = tray.o.z;
+                            r.dx = tray.d.x; r.dy = tray.d.y; r.dz = tray.d.z;
+                            r.t = acc.best_t;
+                            r.pos = acc.best_pos;
+                            r.parent = (int)node_index;
+                            r.slot = child;
+                            r.pad = 0;
+                            rays_out[q] = r;
+                        } else {
+                            counts->overflow = 1u;
                         }
                     }
                 }
-                surface = surface + lit;  // fold(Color::BLACK, Color::add)
             }
-        }
 
-        // ---- the node record ---------------------------------------------------------------------------
-        if (alive) {
-            WfNode<T> nd;
-            nd.parent = parent;
-            nd.slot = slot;
-            nd.pixel = (unsigned)out_index;
-            nd.flags = flags & FR_SCHLICK;
-            nd.k_reflect = k_reflect;
-            nd.k_transparent = k_transparent;
-            nd.reflectance = reflectance;
-            nd.surface[0] = surface.x; nd.surface[1] = surface.y; nd.surface[2] = surface.z;
-            nd.reflected[0] = nd.reflected[1] = nd.reflected[2] = T(0);  // world.rs:121
-            nd.refracted[0] = nd.refracted[1] = nd.refracted[2] = T(0);  // world.rs:137,146
-            nodes[node_index] = nd;
-        }
-
-        // ---- children (world.rs:114-157): trace now, queue the ones that hit -------------------------------
-#pragma unroll 1
-        for (int child = 0; child < 2; ++child) {
-            const bool spawn = alive && (flags & (child == 0 ? FR_REFLECT : FR_REFRACT));
-            if (!__any_sync(0xffffffffu, spawn)) continue;
-            Ray<T> cray;
-            cray.o = child == 0 ? over : under;         // world.rs:124 / world.rs:152
-            cray.d = child == 0 ? reflect_dir : refr_d;
-            if (spawn) {
-                if (child == 0) ++c_reflect;
-                else ++c_refract;
-            }
-            wf_reset_acc(acc, spawn ? MODE_RADIANCE : MODE_IDLE, cray, Real<T>::max());
-            wf_trace<T, FULL, BVH>(sv, cray, acc);
-            const bool child_hit = spawn && acc.best_pos >= 0;
-            const unsigned queued = __ballot_sync(0xffffffffu, child_hit);
-            if (queued) {
-                unsigned qbase = 0;
-                if (lane == 0) qbase = atomicAdd(&counts->n_rays[level + 1], (unsigned)__popc(queued));
-                qbase = __shfl_sync(0xffffffffu, qbase, 0);
-                const unsigned q = qbase + __popc(queued & ((1u << lane) - 1u));
-                if (child_hit) {
-                    if (q < cap_rays) {
-                        WfRay<T> r;
-                        r.ox = cray.o.x; r.oy = cray.o.y; r.oz = cray.o.z;
-                        r.dx = cray.d.x; r.dy = cray.d.y; r.dz = cray.d.z;
-                        r.t = acc.best_t;
-                        r.pos = acc.best_pos;
-                        r.parent = (int)node_index;
-                        r.slot = child;
-                        r.pad = 0;
-                        rays_out[q] = r;
-                    } else {
-                        counts->overflow = 1u;
-                    }
-                }
+            if (phase == 1 + n_lights && alive) {
+                // ---- the node record: complete once the last light has been added ------------------------
+                WfNode<T> nd;
+                nd.parent = parent;
+                nd.slot = slot;
+                nd.pixel = (unsigned)out_index;
+                nd.flags = flags & FR_SCHLICK;
+                nd.k_reflect = k_reflect;
+                nd.k_transparent = k_transparent;
+                nd.reflectance = reflectance;
+                nd.surface[0] = surface.x; nd.surface[1] = surface.y; nd.surface[2] = surface.z;
+                nd.reflected[0] = nd.reflected[1] = nd.reflected[2] = T(0);  // world.rs:121
+                nd.refracted[0] = nd.refracted[1] = nd.refracted[2] = T(0);  // world.rs:137,146
+                nodes[node_index] = nd;
             }
         }
     }
