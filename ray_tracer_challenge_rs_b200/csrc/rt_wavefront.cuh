@@ -18,6 +18,13 @@
 //                    by the parent's reflectiveness / transparency (world.rs:127,156), into the parent's
 //                    slot — or into the pixel for level 0.
 //
+// Two refinements keep warps full and HBM traffic low:
+//   * a queue is filled from both ends — hits on opaque materials from the front, hits on transparent
+//     materials from the back — so a warp of a deeper launch is all-opaque or all-glass and the container
+//     and refraction phases are skipped by whole warps instead of running for one or two lanes;
+//   * a node without children (no iterations left, or a matte material) never becomes a record: its colour
+//     is final when its light loop ends and goes straight into the parent's slot (or the pixel).
+//
 // Every arithmetic operation of a node is the one the persistent kernel (and the reference) performs, in
 // the same order; only WHEN a node is evaluated changes.  The critical path is max_depth+1 launches
 // instead of the longest ray chain, lanes of a warp are always in the same phase, and sibling rays stay
@@ -33,6 +40,7 @@ template <typename T>
 struct WfRay {
     T ox, oy, oz, dx, dy, dz;
     T t;         // hit distance (Intersections::hit, intersections.rs:13-18)
+    T k;         // the parent's reflectiveness (slot 0) / transparency (slot 1): scales the colour sent back
     int pos;     // sorted position of the hit shape
     int parent;  // node that spawned the ray
     int slot;    // 0: its reflected colour, 1: its refracted colour
@@ -45,7 +53,8 @@ struct WfNode {
     int slot;         // slot in the parent (0 reflected, 1 refracted); level 0: unused
     unsigned pixel;   // level 0: output index of the pixel
     int flags;        // FR_SCHLICK
-    T k_reflect, k_transparent, reflectance;
+    T k_parent;       // scale applied to this node's colour when it is handed to the parent (world.rs:127,156)
+    T reflectance;
     T surface[3];
     T reflected[3];   // already scaled by k_reflect (world.rs:127); black until a child reports
     T refracted[3];   // already scaled by k_transparent (world.rs:156)
@@ -53,7 +62,8 @@ struct WfNode {
 
 // Device-side bookkeeping of one frame.
 struct WfCounts {
-    unsigned n_rays[16 + 2];   // rays queued for level d (level 0 = pixels, generated on the fly)
+    unsigned n_rays[16 + 2];   // hits queued for level d at the FRONT of its queue: opaque materials
+    unsigned n_back[16 + 2];   // hits queued for level d at the BACK of its queue: transparent materials
     unsigned node_end[16 + 2]; // nodes created by levels 0..d end at node_end[d] (node_end[-1] = 0 implied)
     unsigned n_nodes;          // nodes allocated so far
     unsigned work;             // chunk cursor of the running launch
@@ -161,7 +171,18 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t tiles_x = (cam.hsize + TILE_W - 1) / TILE_W;
     const uint32_t tiles_y = (cam.n_rows + TILE_H - 1) / TILE_H;
-    const unsigned n_items = level == 0 ? tiles_x * tiles_y * (TILE_W * TILE_H) : min(counts->n_rays[level], cap_rays);
+    // level > 0: front entries, padding to a warp boundary, then back entries
+    unsigned n_front = 0, n_back = 0;
+    if (level > 0) {
+        n_front = counts->n_rays[level];
+        n_back = counts->n_back[level];
+        if ((unsigned long long)n_front + n_back > cap_rays) {  // the producer overflowed (it has flagged it): stay in bounds
+            n_front = min(n_front, cap_rays);
+            n_back = min(n_back, cap_rays - n_front);
+        }
+    }
+    const unsigned front_padded = (n_front + 31u) & ~31u;
+    const unsigned n_items = level == 0 ? tiles_x * tiles_y * (TILE_W * TILE_H) : front_padded + n_back;
     const int n_lights = (int)layout.n_lights;
     const int remaining = (int)cam.max_depth - level;
     unsigned int c_primary = 0, c_shadow = 0, c_reflect = 0, c_refract = 0, c_nodes = 0;
@@ -182,7 +203,7 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
         int parent = -1, slot = 0;
         size_t out_index = 0;
         int queued_pos = -1;
-        T queued_t = T(0);
+        T queued_t = T(0), k_parent = T(1);
         if (level == 0) {
             if (active) {
                 const uint32_t tile = item / (TILE_W * TILE_H), in = item % (TILE_W * TILE_H);
@@ -204,15 +225,18 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                     ++c_primary;
                 }
             }
-        } else if (active) {
+        } else if (active && (item < n_front || item >= front_padded)) {
             // the parent's launch already traced this ray and only queued it because it hit
-            const WfRay<T> r = rays_in[item];
+            const WfRay<T> r = rays_in[item < n_front ? item : cap_rays - 1u - (item - front_padded)];
             ray.o = mk<T>(r.ox, r.oy, r.oz);
             ray.d = mk<T>(r.dx, r.dy, r.dz);
             parent = r.parent;
             slot = r.slot;
+            k_parent = r.k;
             queued_pos = r.pos;
             queued_t = r.t;
+        } else {
+            active = false;  // padding between the two ends of the queue
         }
 
         // per-node state, filled phase by phase
@@ -279,16 +303,7 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                 }
                 const bool hit = active && acc.best_pos >= 0;
                 if (level == 0 && active && !hit) wf_store_pixel(out_rgb, out_rgb8, out_index, mk<T>(T(0), T(0), T(0)));  // World::DEFAULT_COLOR
-                const unsigned hits = __ballot_sync(0xffffffffu, hit);
-                unsigned node_base = 0;
-                if (lane == 0 && hits) node_base = atomicAdd(&counts->n_nodes, (unsigned)__popc(hits));
-                node_base = __shfl_sync(0xffffffffu, node_base, 0);
-                node_index = node_base + __popc(hits & ((1u << lane) - 1u));
                 alive = hit;
-                if (hit && node_index >= cap_nodes) {
-                    counts->overflow = 1u;
-                    alive = false;
-                }
                 if (alive) {  // intersection.rs:21-31, computed_hit.rs:33-34
                     ++c_nodes;
                     hit_pos = acc.best_pos;
@@ -392,18 +407,30 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
             } else {
                 // ---- a child that hit something becomes a work item of the next level -----------------------
                 const bool child_hit = spawn && acc.best_pos >= 0;
-                const unsigned queued = __ballot_sync(0xffffffffu, child_hit);
-                if (queued) {
-                    unsigned qbase = 0;
-                    if (lane == 0) qbase = atomicAdd(&counts->n_rays[level + 1], (unsigned)__popc(queued));
-                    qbase = __shfl_sync(0xffffffffu, qbase, 0);
-                    const unsigned q = qbase + __popc(queued & ((1u << lane) - 1u));
+                // which end of the next queue: does the child's hit need the container / refraction phases?
+                const bool glass = child_hit && sv.material((uint32_t)sv.shape_meta((uint32_t)acc.best_pos).y)[MAT_TRANSPARENCY] != T(0);
+                const unsigned queued_front = __ballot_sync(0xffffffffu, child_hit && !glass);
+                const unsigned queued_back = __ballot_sync(0xffffffffu, glass);
+                if (queued_front | queued_back) {
+                    unsigned fbase = 0, bbase = 0;
+                    if (lane == 0) {
+                        if (queued_front) fbase = atomicAdd(&counts->n_rays[level + 1], (unsigned)__popc(queued_front));
+                        if (queued_back) bbase = atomicAdd(&counts->n_back[level + 1], (unsigned)__popc(queued_back));
+                    }
+                    fbase = __shfl_sync(0xffffffffu, fbase, 0);
+                    bbase = __shfl_sync(0xffffffffu, bbase, 0);
                     if (child_hit) {
-                        if (q < cap_rays) {
+                        const unsigned below = (1u << lane) - 1u;
+                        const unsigned f = fbase + __popc(queued_front & below), bk = bbase + __popc(queued_back & below);
+                        // both ends grow towards each other; wf_advance_kernel compares their sum with the capacity
+                        // once the launch is over (an overlap garbles entries of a frame that is re-rendered anyway)
+                        const unsigned q = glass ? cap_rays - 1u - bk : f;
+                        if ((glass ? bk : f) < cap_rays) {
                             WfRay<T> r;
                             r.ox = tray.o.x; r.oy = tray.o.y; r.oz = tray.o.z;
                             r.dx = tray.d.x; r.dy = tray.d.y; r.dz = tray.d.z;
                             r.t = acc.best_t;
+                            r.k = child == 0 ? k_reflect : k_transparent;
                             r.pos = acc.best_pos;
                             r.parent = (int)node_index;
                             r.slot = child;
@@ -416,20 +443,41 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                 }
             }
 
-            if (phase == 1 + n_lights && alive) {
-                // ---- the node record: complete once the last light has been added ------------------------
-                WfNode<T> nd;
-                nd.parent = parent;
-                nd.slot = slot;
-                nd.pixel = (unsigned)out_index;
-                nd.flags = flags & FR_SCHLICK;
-                nd.k_reflect = k_reflect;
-                nd.k_transparent = k_transparent;
-                nd.reflectance = reflectance;
-                nd.surface[0] = surface.x; nd.surface[1] = surface.y; nd.surface[2] = surface.z;
-                nd.reflected[0] = nd.reflected[1] = nd.reflected[2] = T(0);  // world.rs:121
-                nd.refracted[0] = nd.refracted[1] = nd.refracted[2] = T(0);  // world.rs:137,146
-                nodes[node_index] = nd;
+            if (phase == 1 + n_lights) {
+                // ---- the light loop is over: a node without children is finished, the others get a record ----
+                const bool interior = alive && (flags & (FR_REFLECT | FR_REFRACT));
+                const unsigned records = __ballot_sync(0xffffffffu, interior);
+                if (records) {
+                    unsigned node_base = 0;
+                    if (lane == 0) node_base = atomicAdd(&counts->n_nodes, (unsigned)__popc(records));
+                    node_base = __shfl_sync(0xffffffffu, node_base, 0);
+                    node_index = node_base + __popc(records & ((1u << lane) - 1u));
+                }
+                if (interior && node_index >= cap_nodes) {
+                    counts->overflow = 1u;
+                    flags &= ~(FR_REFLECT | FR_REFRACT);  // no record, no children: the frame is re-rendered anyway
+                } else if (interior) {
+                    WfNode<T> nd;
+                    nd.parent = parent;
+                    nd.slot = slot;
+                    nd.pixel = (unsigned)out_index;
+                    nd.flags = flags & FR_SCHLICK;
+                    nd.k_parent = k_parent;
+                    nd.reflectance = reflectance;
+                    nd.surface[0] = surface.x; nd.surface[1] = surface.y; nd.surface[2] = surface.z;
+                    nd.reflected[0] = nd.reflected[1] = nd.reflected[2] = T(0);  // world.rs:121
+                    nd.refracted[0] = nd.refracted[1] = nd.refracted[2] = T(0);  // world.rs:137,146
+                    nodes[node_index] = nd;
+                } else if (alive) {
+                    // world.rs:59-66 with black children: (surface + 0) + 0 — and 0 * reflectance is 0 too — is `surface`
+                    if (parent < 0) {
+                        wf_store_pixel(out_rgb, out_rgb8, out_index, surface);
+                    } else {
+                        const V3<T> c = surface * k_parent;  // world.rs:127 / 156
+                        T* dst = slot == 0 ? nodes[parent].reflected : nodes[parent].refracted;
+                        dst[0] = c.x; dst[1] = c.y; dst[2] = c.z;
+                    }
+                }
             }
         }
     }
@@ -451,9 +499,10 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
 }
 
 // Called between levels: remember where this level's nodes end, reset the chunk cursor.
-__global__ void wf_advance_kernel(WfCounts* counts, int level) {
+__global__ void wf_advance_kernel(WfCounts* counts, int level, unsigned cap_rays) {
     counts->node_end[level] = counts->n_nodes;
     counts->work = 0u;
+    if ((unsigned long long)counts->n_rays[level + 1] + counts->n_back[level + 1] > cap_rays) counts->overflow = 1u;
 }
 
 // World::shade_hit's tail (world.rs:59-66) for the nodes of one level, deepest level first.
@@ -473,14 +522,9 @@ __global__ void wf_combine_kernel(WfNode<T>* __restrict__ nodes, const WfCounts*
         if (n.parent < 0) {
             wf_store_pixel(out_rgb, out_rgb8, (size_t)n.pixel, colour);  // Camera::render_parallel, camera.rs:108
         } else {
-            WfNode<T>& p = nodes[n.parent];
-            if (n.slot == 0) {
-                const V3<T> c = colour * p.k_reflect;  // world.rs:127
-                p.reflected[0] = c.x; p.reflected[1] = c.y; p.reflected[2] = c.z;
-            } else {
-                const V3<T> c = colour * p.k_transparent;  // world.rs:156
-                p.refracted[0] = c.x; p.refracted[1] = c.y; p.refracted[2] = c.z;
-            }
+            const V3<T> c = colour * n.k_parent;  // world.rs:127 / 156
+            T* dst = n.slot == 0 ? nodes[n.parent].reflected : nodes[n.parent].refracted;
+            dst[0] = c.x; dst[1] = c.y; dst[2] = c.z;
         }
     }
 }

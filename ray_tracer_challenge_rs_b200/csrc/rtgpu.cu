@@ -622,7 +622,7 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
         level_kernel<<<grid, RT_WF_THREADS, smem, stream>>>(d_reals, ctx->d_ints, lay, cam, level, in, out, (unsigned)ctx->wf_cap_rays, nodes,
                                                             (unsigned)ctx->wf_cap_nodes, ctx->d_wf_counts, d_out, d_out8, ctx->d_wf_priv);
         CUDA_TRY(cudaGetLastError());
-        rt::wf_advance_kernel<<<1, 1, 0, stream>>>(ctx->d_wf_counts, level);
+        rt::wf_advance_kernel<<<1, 1, 0, stream>>>(ctx->d_wf_counts, level, (unsigned)ctx->wf_cap_rays);
         CUDA_TRY(cudaGetLastError());
     }
     for (int level = levels - 1; level >= 0; --level)
@@ -657,7 +657,7 @@ int wavefront_check(rtgpu_context* ctx, uint64_t pixels, cudaStream_t stream) {
     if (!h.overflow) return 0;
     // what the frame actually asked for, with headroom
     unsigned max_rays = 0;
-    for (int d = 0; d < 18; ++d) max_rays = std::max(max_rays, h.n_rays[d]);
+    for (int d = 0; d < 18; ++d) max_rays = std::max(max_rays, h.n_rays[d] + h.n_back[d]);
     const double g_rays = (double)max_rays / (3.0 * (double)pixels), g_nodes = (double)h.n_nodes / (5.0 * (double)pixels);
     const double growth = std::max(1.25 * std::max(g_rays, g_nodes), 2.0 * (double)ctx->wf_cap_rays / (3.0 * (double)pixels));
     int st = wavefront_reserve<T>(ctx, pixels, growth);
