@@ -165,8 +165,10 @@ typedef struct rtgpu_opts {
 } rtgpu_opts;
 
 #define RTGPU_FLAG_NONE 0u
-/* Kernel family (both produce the same pixels).  Default: RTGPU_WAVEFRONT=0/1 in the environment, else the
- * library's built-in choice.
+/* Kernel family (both produce the same pixels and counters, bit for bit).  Neither flag = auto: RTGPU_FAMILY=
+ * persistent|wavefront|auto in the environment, else the library measures — for each (scene, frame shape) a
+ * context times its first two frames of each family with CUDA events and renders the rest with the faster
+ * one; scenes without reflective or transparent materials always take PERSISTENT.
  *   PERSISTENT : one launch; every lane walks one pixel's recursion tree with an explicit stack.
  *   WAVEFRONT  : one launch per recursion level over queues of rays (+ a bottom-up combine per level).
  *                rtgpu_context_render_device then blocks until the frame is complete (it has to verify that
@@ -233,11 +235,15 @@ int rtgpu_context_render(rtgpu_context *context, const rtgpu_camera *camera, con
                          const rtgpu_rows *rows, double *out_rgb, uint8_t *out_rgb8,
                          rtgpu_stats *stats);
 
+/* Kernel family the calling thread's most recent render ran: 0 = persistent, 1 = wavefront (what the automatic
+ * choice settled on; benchmarks report it). */
+int rtgpu_last_family(void);
+
 /* -- pinned host memory ---------------------------------------------------------------------- */
 /* Page-locked, device-mapped host memory.  When out_rgb / out_rgb8 of a host-buffer render live in such
- * memory (these functions, cudaHostAlloc, cudaHostRegister, torch pin_memory ...) the kernels write the
- * finished pixels straight into them over PCIe while the render is still running (no staging copy);
- * ordinary pageable buffers work too, through a device staging buffer and a copy. */
+ * memory (these functions, cudaHostAlloc, cudaHostRegister, torch pin_memory ...) the persistent kernel writes
+ * the finished pixels straight into them over PCIe while the render is still running (no staging copy);
+ * ordinary pageable buffers — and the wavefront family — go through a device staging buffer and a copy. */
 void *rtgpu_host_alloc(size_t bytes);
 void rtgpu_host_free(void *ptr);
 

@@ -133,6 +133,7 @@ EXPORTED_SYMBOLS = (
     "rtgpu_context_destroy",
     "rtgpu_context_render_device",
     "rtgpu_context_render",
+    "rtgpu_last_family",
     "rtgpu_host_alloc",
     "rtgpu_host_free",
     "rtgpu_measure_fma_peak",
@@ -209,6 +210,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     ]
     lib.rtgpu_measure_fma_peak.restype = C.c_int
     lib.rtgpu_measure_fma_peak.argtypes = [C.c_int, C.c_uint32, _pd, _pd]
+    lib.rtgpu_last_family.restype = C.c_int
+    lib.rtgpu_last_family.argtypes = []
     lib.rtgpu_host_alloc.restype = C.c_void_p
     lib.rtgpu_host_alloc.argtypes = [C.c_size_t]
     lib.rtgpu_host_free.restype = None

@@ -702,7 +702,7 @@ RT_COLD V3<T> local_normal_at(const SceneView<T>& sv, uint32_t pos, int type, co
 
 // Rust `f64 as i64` (saturating, NaN -> 0) followed by `% 2 == 0`
 template <typename T>
-RT_DEV bool even_as_i64(T v) {
+RT_COLD bool even_as_i64(T v) {
     if (v != v) return true;                               // NaN as i64 = 0
     if (v >= T(9223372036854775808.0)) return false;       // saturates to i64::MAX (odd)
     if (v <= T(-9223372036854775808.0)) return true;       // saturates to i64::MIN (even)
@@ -724,7 +724,7 @@ RT_COLD V3<T> pattern_color_at(const SceneView<T>& sv, int pattern, V3<T> p) {
             if (!even_as_i64(p.x)) fraction = T(1) - fraction;
             return a + (distance * fraction);
         }
-        case 2: return even_as_i64(floor(sqrt(sq(p.x) + sq(p.z)))) ? a : b;   // ring_pattern.rs:25-32
+        case 2: return even_as_i64(floor(sqrt_native(sq(p.x) + sq(p.z)))) ? a : b;   // ring_pattern.rs:25-32
         case 3: return even_as_i64(floor(p.x) + floor(p.y) + floor(p.z)) ? a : b;  // checker_pattern.rs:24-31
         case 4: pattern = even_as_i64(floor(p.x)) ? pm[1] : pm[2]; break;  // complex_pattern.rs:24-33
         default: return p;                                                 // TestPattern, pattern.rs:62-66

@@ -70,6 +70,9 @@ struct WfCounts {
     unsigned overflow;         // a queue or the node array was too small: the frame must be re-rendered
 };
 
+#ifndef RT_WF_SYNC
+#define RT_WF_SYNC 0
+#endif
 #ifndef RT_WF_THREADS
 #define RT_WF_THREADS 128
 #endif
@@ -189,11 +192,23 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
 
     for (;;) {
         // one warp = 32 consecutive work items (one 8x4 tile of pixels, or 32 neighbouring queue entries)
+#if RT_WF_SYNC
+        // CTA-wide lockstep: the whole CTA takes blockDim.x consecutive items and walks the phases together
+        // (barrier per phase), so that the warps of an SM execute — and fetch — the same code at the same time
+        __shared__ unsigned cta_first;
+        __syncthreads();
+        if (threadIdx.x == 0) cta_first = atomicAdd(&counts->work, blockDim.x);
+        __syncthreads();
+        const unsigned first = cta_first + (threadIdx.x & ~31u);
+        if (cta_first >= n_items) break;
+        const unsigned item = first + lane;
+#else
         unsigned first = 0;
         if (lane == 0) first = atomicAdd(&counts->work, 32u);
         first = __shfl_sync(0xffffffffu, first, 0);
         if (first >= n_items) break;
         const unsigned item = first + lane;
+#endif
 
         // ---- the radiance ray of this work item -------------------------------------------------
         bool active = item < n_items;
@@ -257,6 +272,9 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
         const int n_phases = 4 + n_lights;
 #pragma unroll 1
         for (int phase = 0; phase < n_phases; ++phase) {
+#if RT_WF_SYNC
+            __syncthreads();
+#endif
             Ray<T> tray = ray;
             int mode = MODE_IDLE;
             T seed = Real<T>::max();

@@ -53,6 +53,8 @@ struct PackedScene {
     std::vector<int> ints;
     rt::SceneLayout layout;
     bool has_cyl_cone_tri = false;
+    bool has_secondary = false;  // some material is reflective or transparent: rays beyond primary + shadow exist
+    uint64_t fingerprint = 0;    // of the packed blobs (sampled for large scenes): the tuner's notion of "same scene"
 };
 
 int validate_scene(const rtgpu_scene* s) {
@@ -329,6 +331,10 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
         n_tri += s->shape_type[i] == RTGPU_TRIANGLE ? 1u : 0u;
         if (s->shape_type[i] >= RTGPU_CYLINDER) out->has_cyl_cone_tri = true;
     }
+    for (uint32_t m = 0; m < M; ++m) {
+        const double* prm = s->mat_params + (size_t)m * RTGPU_MAT_PARAM_COUNT;
+        if (prm[4] > 0.0 || prm[5] > 0.0) out->has_secondary = true;  // reflective, transparency (world.rs:121, 137)
+    }
     const uint32_t n_nodes = (uint32_t)bvh.nodes.size();
     lay.n_bvh_nodes = use_bvh ? std::max(n_nodes, 1u) : 0u;  // a single bounded shape still gets one (half-empty) node
     lay.bvh_root = 0;
@@ -442,6 +448,19 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
             I[lay.bvh_meta_off + k * rt::BVH_INTS + 1] = leaf_ref(bvh.nodes[k].child[1]);
         }
     }
+    // FNV-1a over (a sample of) the blobs: tells the family tuner whether two uploads are the same scene
+    uint64_t fp = 1469598103934665603ull;
+    auto mix = [&fp](uint64_t v) { fp = (fp ^ v) * 1099511628211ull; };
+    mix(lay.n_reals);
+    mix(lay.n_ints);
+    const size_t step_r = std::max<size_t>(1, out->reals.size() >> 15), step_i = std::max<size_t>(1, out->ints.size() >> 15);
+    for (size_t k = 0; k < out->reals.size(); k += step_r) {
+        uint64_t bits;
+        memcpy(&bits, &out->reals[k], sizeof(bits));
+        mix(bits);
+    }
+    for (size_t k = 0; k < out->ints.size(); k += step_i) mix((uint64_t)(uint32_t)out->ints[k]);
+    out->fingerprint = fp;
     return RTGPU_OK;
 }
 
@@ -507,6 +526,19 @@ struct rtgpu_context {
     size_t wf_cap_rays = 0, wf_cap_nodes = 0;  // in elements
     size_t wf_bytes_rays = 0, wf_bytes_nodes = 0;
     bool wf_used = false;  // the last launch took the wavefront path (overflow must be checked after it)
+    // kernel-family tuner (FAMILY_AUTO): per (scene, frame shape, path) the best time of each family
+    bool has_secondary = false;
+    uint64_t scene_fingerprint = 0;
+    struct TuneEntry {
+        uint64_t key = 0;
+        float best_ms[2] = {1e30f, 1e30f};
+        int runs[2] = {0, 0};
+    };
+    std::vector<TuneEntry> tune;
+    cudaEvent_t tune_ev0 = nullptr, tune_ev1 = nullptr;
+    int tune_pending_family = -1;  // a trial whose events have been recorded but not read yet
+    uint64_t tune_pending_key = 0;
+    int last_family = 0;
 };
 
 namespace {
@@ -548,12 +580,98 @@ __global__ void wf_commit_counters_kernel(const unsigned long long* priv, unsign
     if (threadIdx.x < rt::NUM_COUNTERS && priv[threadIdx.x]) atomicAdd(&user[threadIdx.x], priv[threadIdx.x]);
 }
 
-bool wavefront_requested(const rtgpu_opts* opts) {
-    if (opts && (opts->flags & RTGPU_FLAG_PERSISTENT)) return false;
-    if (opts && (opts->flags & RTGPU_FLAG_WAVEFRONT)) return true;
+enum { FAMILY_PERSISTENT = 0, FAMILY_WAVEFRONT = 1, FAMILY_AUTO = 2 };
+thread_local int g_last_family = FAMILY_PERSISTENT;
+
+// What the caller asked for: opts.flags, else RTGPU_FAMILY=persistent|wavefront|auto (or RTGPU_WAVEFRONT=0/1), else auto.
+int requested_family(const rtgpu_opts* opts) {
+    if (opts && (opts->flags & RTGPU_FLAG_PERSISTENT)) return FAMILY_PERSISTENT;
+    if (opts && (opts->flags & RTGPU_FLAG_WAVEFRONT)) return FAMILY_WAVEFRONT;
+    const char* f = getenv("RTGPU_FAMILY");
+    if (f && *f) {
+        if (f[0] == 'p') return FAMILY_PERSISTENT;
+        if (f[0] == 'w') return FAMILY_WAVEFRONT;
+        return FAMILY_AUTO;
+    }
     const char* e = getenv("RTGPU_WAVEFRONT");
-    if (e && *e) return e[0] != '0';
-    return RTGPU_DEFAULT_WAVEFRONT != 0;
+    if (e && *e) return e[0] != '0' ? FAMILY_WAVEFRONT : FAMILY_PERSISTENT;
+    return RTGPU_DEFAULT_WAVEFRONT != 0 ? FAMILY_WAVEFRONT : FAMILY_AUTO;
+}
+
+// ---- family tuner ----------------------------------------------------------------------------------
+// Which family is faster depends on the scene (how much the per-pixel work varies) and on how many pixels one
+// launch covers, and no static rule we tried predicts it.  So FAMILY_AUTO measures: the first TUNE_RUNS frames of
+// each family for a given (scene, frame shape, path) are timed with CUDA events on the stream they run on,
+// alternating P, W, P, W; after that the faster family renders every frame.  Both families produce the same
+// pixels and counters bit for bit (tests/test_gpu_parity.py), so the choice is invisible apart from the time.
+constexpr int TUNE_RUNS = 2;
+
+uint64_t tune_key(const rtgpu_context* ctx, const rtgpu_camera* camera, const RowSel& sel, uint32_t precision, uint32_t max_depth, uint32_t path) {
+    uint64_t k = ctx->scene_fingerprint;
+    auto mix = [&k](uint64_t v) { k = (k ^ v) * 1099511628211ull; };
+    mix(camera->hsize);
+    mix(camera->vsize);
+    mix(sel.band_rows);
+    mix(sel.shard_count);
+    mix(precision);
+    mix(max_depth);
+    mix(path);
+    return k ? k : 1;
+}
+
+void tune_collect(rtgpu_context* ctx) {
+    if (ctx->tune_pending_family < 0) return;
+    const int family = ctx->tune_pending_family;
+    ctx->tune_pending_family = -1;
+    float ms = 0.f;
+    if (cudaEventSynchronize(ctx->tune_ev1) != cudaSuccess || cudaEventElapsedTime(&ms, ctx->tune_ev0, ctx->tune_ev1) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    for (auto& e : ctx->tune)
+        if (e.key == ctx->tune_pending_key) {
+            e.best_ms[family] = std::min(e.best_ms[family], ms);
+            e.runs[family]++;
+            return;
+        }
+}
+
+// Family for this frame; *trial = the caller should bracket the frame with tune_begin / tune_end.
+int resolve_family(rtgpu_context* ctx, const rtgpu_opts* opts, uint64_t key, bool* trial) {
+    *trial = false;
+    const int want = requested_family(opts);
+    if (want != FAMILY_AUTO) return want;
+    if (!ctx->has_secondary) return FAMILY_PERSISTENT;  // primary + shadow rays only: one level, nothing for the queues to even out
+    tune_collect(ctx);
+    rtgpu_context::TuneEntry* entry = nullptr;
+    for (auto& e : ctx->tune)
+        if (e.key == key) entry = &e;
+    if (!entry) {
+        if (ctx->tune.size() >= 64) ctx->tune.erase(ctx->tune.begin());
+        ctx->tune.emplace_back();
+        entry = &ctx->tune.back();
+        entry->key = key;
+    }
+    if (entry->runs[0] < TUNE_RUNS || entry->runs[1] < TUNE_RUNS) {
+        if (!ctx->tune_ev0 && (cudaEventCreate(&ctx->tune_ev0) != cudaSuccess || cudaEventCreate(&ctx->tune_ev1) != cudaSuccess)) {
+            cudaGetLastError();
+            return FAMILY_PERSISTENT;
+        }
+        *trial = true;
+        return (entry->runs[0] <= entry->runs[1] && entry->runs[0] < TUNE_RUNS) ? FAMILY_PERSISTENT : FAMILY_WAVEFRONT;
+    }
+    return entry->best_ms[FAMILY_WAVEFRONT] < entry->best_ms[FAMILY_PERSISTENT] ? FAMILY_WAVEFRONT : FAMILY_PERSISTENT;
+}
+
+void tune_begin(rtgpu_context* ctx, cudaStream_t stream) { cudaEventRecord(ctx->tune_ev0, stream); }
+
+void tune_end(rtgpu_context* ctx, cudaStream_t stream, uint64_t key, int family) {
+    if (cudaEventRecord(ctx->tune_ev1, stream) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    ctx->tune_pending_family = family;
+    ctx->tune_pending_key = key;
 }
 
 template <typename T>
@@ -751,7 +869,7 @@ int render_wavefront(rtgpu_context* ctx, const T* d_reals, const rt::CameraParam
 
 int render_device_impl(rtgpu_context* ctx, const rtgpu_camera* camera, const rtgpu_opts* opts, const rtgpu_rows* rows,
                        void* d_out_rgb, uint8_t* d_out_rgb8, uint64_t* d_counters, cudaStream_t stream, uint32_t* out_n_rows,
-                       bool full_frame_out = false, bool wavefront_blocking = true) {
+                       int family, bool full_frame_out = false, bool wavefront_blocking = true) {
     if (!ctx || !camera) return fail(RTGPU_ERR_INVALID_ARGUMENT, "context or camera is NULL");
     if (!d_out_rgb && !d_out_rgb8) return fail(RTGPU_ERR_INVALID_ARGUMENT, "both output pointers are NULL");
     uint32_t precision, max_depth;
@@ -765,10 +883,12 @@ int render_device_impl(rtgpu_context* ctx, const rtgpu_camera* camera, const rtg
     if (n_rows == 0 || camera->hsize == 0) return RTGPU_OK;  // nothing to render
     CUDA_TRY(cudaSetDevice(ctx->device));
     unsigned long long* counters = reinterpret_cast<unsigned long long*>(d_counters);
+    const bool wavefront = family == FAMILY_WAVEFRONT;
+    ctx->last_family = g_last_family = wavefront ? FAMILY_WAVEFRONT : FAMILY_PERSISTENT;
     if (precision == RTGPU_PRECISION_F64) {
         rt::CameraParams<double> cam;
         fill_camera(camera, sel, n_rows, max_depth, full_frame_out, &cam);
-        if (wavefront_requested(opts)) return render_wavefront<double>(ctx, ctx->d_reals64, cam, (double*)d_out_rgb, d_out_rgb8, counters, stream, wavefront_blocking);
+        if (wavefront) return render_wavefront<double>(ctx, ctx->d_reals64, cam, (double*)d_out_rgb, d_out_rgb8, counters, stream, wavefront_blocking);
         if (max_depth <= 7) return launch_kernel<double, 8>(ctx, ctx->d_reals64, cam, (double*)d_out_rgb, d_out_rgb8, counters, stream);
         return launch_kernel<double, 16>(ctx, ctx->d_reals64, cam, (double*)d_out_rgb, d_out_rgb8, counters, stream);
     }
@@ -776,7 +896,7 @@ int render_device_impl(rtgpu_context* ctx, const rtgpu_camera* camera, const rtg
     if (st != RTGPU_OK) return st;
     rt::CameraParams<float> cam;
     fill_camera(camera, sel, n_rows, max_depth, full_frame_out, &cam);
-    if (wavefront_requested(opts)) return render_wavefront<float>(ctx, ctx->d_reals32, cam, (float*)d_out_rgb, d_out_rgb8, counters, stream, wavefront_blocking);
+    if (wavefront) return render_wavefront<float>(ctx, ctx->d_reals32, cam, (float*)d_out_rgb, d_out_rgb8, counters, stream, wavefront_blocking);
     if (max_depth <= 7) return launch_kernel<float, 8>(ctx, ctx->d_reals32, cam, (float*)d_out_rgb, d_out_rgb8, counters, stream);
     return launch_kernel<float, 16>(ctx, ctx->d_reals32, cam, (float*)d_out_rgb, d_out_rgb8, counters, stream);
 }
@@ -787,6 +907,8 @@ int upload_scene(rtgpu_context* ctx, const PackedScene& packed) {
     ctx->d_reals32 = nullptr;
     ctx->layout = lay;
     ctx->has_cyl_cone_tri = packed.has_cyl_cone_tri;
+    ctx->has_secondary = packed.has_secondary;
+    ctx->scene_fingerprint = packed.fingerprint;
     // repeated frames of similar scenes reuse the allocations (cudaFree / cudaMalloc synchronise the device)
     const size_t need_reals = std::max<size_t>(16, (size_t)lay.n_reals * sizeof(double));
     const size_t need_ints = std::max<size_t>(16, (size_t)lay.n_ints * sizeof(int));
@@ -848,6 +970,8 @@ void context_release(rtgpu_context* ctx) {
     if (ctx->d_wf_priv) cudaFree(ctx->d_wf_priv);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->tune_ev0) cudaEventDestroy(ctx->tune_ev0);
+    if (ctx->tune_ev1) cudaEventDestroy(ctx->tune_ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -885,7 +1009,7 @@ void* mapped_device_pointer(const void* host) {
 // Issue (do not wait for) everything one device does for a host-buffer render: kernel + D2H of its
 // row bands into the full-frame host buffers.
 int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rtgpu_opts* opts, const rtgpu_rows* rows,
-                        void* out_rgb, uint8_t* out_rgb8) {
+                        void* out_rgb, uint8_t* out_rgb8, int forced_family = -1) {
     uint32_t precision, max_depth;
     int st = check_opts(opts, &precision, &max_depth);
     if (st != RTGPU_OK) return st;
@@ -897,28 +1021,45 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
     const size_t row_rgb = (size_t)camera->hsize * 3 * elem;
     const size_t row_rgb8 = (size_t)camera->hsize * 3;
     CUDA_TRY(cudaSetDevice(ctx->device));
-    // Zero-copy: when the caller's buffers are pinned, device-mapped host memory the kernel writes each
+    // Zero-copy: when the caller's buffers are pinned, device-mapped host memory the persistent kernel writes each
     // finished pixel straight into the caller's Canvas (full-frame indexing); the PCIe traffic then
-    // overlaps the render instead of following it.  Pageable buffers take the staging path below.
+    // overlaps the render instead of following it.  Pageable buffers take the staging path below, and so does
+    // the wavefront family: it finishes most pixels in its last launches, and that burst of small stores
+    // crosses PCIe far slower than one copy-engine transfer of the finished rows.
     void* map_rgb = out_rgb ? mapped_device_pointer(out_rgb) : nullptr;
     void* map_rgb8 = out_rgb8 ? mapped_device_pointer(out_rgb8) : nullptr;
     const char* zc = getenv("RTGPU_ZEROCOPY");
-    ctx->zero_copy = !(zc && zc[0] == '0') && (!out_rgb || map_rgb) && (!out_rgb8 || map_rgb8);
+    const bool mappable = !(zc && zc[0] == '0') && (!out_rgb || map_rgb) && (!out_rgb8 || map_rgb8);
+    bool trial = false;
+    const uint64_t key = tune_key(ctx, camera, sel, precision, max_depth, 1u + (mappable ? 1u : 0u) + (out_rgb ? 2u : 0u) + (out_rgb8 ? 4u : 0u));
+    const int family = forced_family >= 0 ? forced_family : resolve_family(ctx, opts, key, &trial);
+    ctx->zero_copy = mappable && family == FAMILY_PERSISTENT;
     if (!ctx->zero_copy) {
         st = ensure_out_buffers(ctx, out_rgb ? row_rgb * n_rows : 0, out_rgb8 ? row_rgb8 * n_rows : 0);
         if (st != RTGPU_OK) return st;
     }
+    if (family == FAMILY_WAVEFRONT && n_rows && camera->hsize) {
+        // allocate the queues before the timed region (cudaMalloc waits for the device)
+        const uint64_t pixels = (uint64_t)camera->hsize * n_rows;
+        const size_t ray_bytes = precision == RTGPU_PRECISION_F64 ? sizeof(rt::WfRay<double>) : sizeof(rt::WfRay<float>);
+        if (ctx->wf_bytes_rays / ray_bytes < 3 * pixels / 2) {
+            st = precision == RTGPU_PRECISION_F64 ? wavefront_reserve<double>(ctx, pixels, 1.0) : wavefront_reserve<float>(ctx, pixels, 1.0);
+            if (st != RTGPU_OK) return st;
+        }
+    }
     CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, rt::NUM_COUNTERS * sizeof(unsigned long long), ctx->stream));
+    if (trial) tune_begin(ctx, ctx->stream);
     CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
     if (ctx->zero_copy) {
         st = render_device_impl(ctx, camera, opts, rows, map_rgb, (uint8_t*)map_rgb8, reinterpret_cast<uint64_t*>(ctx->d_counters),
-                                ctx->stream, nullptr, /*full_frame_out=*/true, /*wavefront_blocking=*/false);
+                                ctx->stream, nullptr, family, /*full_frame_out=*/true, /*wavefront_blocking=*/false);
         if (st != RTGPU_OK) return st;
         CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+        if (trial) tune_end(ctx, ctx->stream, key, family);
         return RTGPU_OK;
     }
     st = render_device_impl(ctx, camera, opts, rows, out_rgb ? ctx->d_out : nullptr, out_rgb8 ? ctx->d_out8 : nullptr,
-                            reinterpret_cast<uint64_t*>(ctx->d_counters), ctx->stream, nullptr, false, /*wavefront_blocking=*/false);
+                            reinterpret_cast<uint64_t*>(ctx->d_counters), ctx->stream, nullptr, family, false, /*wavefront_blocking=*/false);
     if (st != RTGPU_OK) return st;
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     // compact band b (rows [b*band_rows, ...)) of this shard -> image rows of band (b*shard_count + shard_index)
@@ -932,6 +1073,7 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
             CUDA_TRY(cudaMemcpyAsync(out_rgb8 + (size_t)y * row_rgb8, ctx->d_out8 + (size_t)k * row_rgb8, row_rgb8 * rows_here,
                                      cudaMemcpyDeviceToHost, ctx->stream));
     }
+    if (trial) tune_end(ctx, ctx->stream, key, family);  // the copies belong to this path's cost
     return RTGPU_OK;
 }
 
@@ -949,7 +1091,7 @@ int finish_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rtg
         st = f64 ? wavefront_check<double>(ctx, pixels, ctx->stream) : wavefront_check<float>(ctx, pixels, ctx->stream);
         if (st < 0) return st;
         if (st == 0) break;
-        st = enqueue_host_render(ctx, camera, opts, rows, out_rgb, out_rgb8);
+        st = enqueue_host_render(ctx, camera, opts, rows, out_rgb, out_rgb8, FAMILY_WAVEFRONT);
         if (st != RTGPU_OK) return st;
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
@@ -1111,8 +1253,25 @@ void rtgpu_context_destroy(rtgpu_context* context) { context_release(context); }
 int rtgpu_context_render_device(rtgpu_context* context, const rtgpu_camera* camera, const rtgpu_opts* opts,
                                 const rtgpu_rows* rows, void* d_out_rgb, uint8_t* d_out_rgb8, uint64_t* d_counters,
                                 void* cuda_stream) {
-    return render_device_impl(context, camera, opts, rows, d_out_rgb, d_out_rgb8, d_counters, (cudaStream_t)cuda_stream, nullptr);
+    if (!context || !camera) return fail(RTGPU_ERR_INVALID_ARGUMENT, "context or camera is NULL");
+    uint32_t precision, max_depth;
+    int st = check_opts(opts, &precision, &max_depth);
+    if (st != RTGPU_OK) return st;
+    RowSel sel;
+    st = normalise_rows(rows, camera->vsize, &sel);
+    if (st != RTGPU_OK) return st;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    bool trial = false;
+    const uint64_t key = tune_key(context, camera, sel, precision, max_depth, 0u);
+    CUDA_TRY(cudaSetDevice(context->device));
+    const int family = resolve_family(context, opts, key, &trial);
+    if (trial) tune_begin(context, stream);
+    st = render_device_impl(context, camera, opts, rows, d_out_rgb, d_out_rgb8, d_counters, stream, nullptr, family);
+    if (trial && st == RTGPU_OK) tune_end(context, stream, key, family);
+    return st;
 }
+
+int rtgpu_last_family(void) { return g_last_family; }
 
 int rtgpu_context_render(rtgpu_context* context, const rtgpu_camera* camera, const rtgpu_opts* opts, const rtgpu_rows* rows,
                          double* out_rgb, uint8_t* out_rgb8, rtgpu_stats* stats) {

@@ -23,10 +23,19 @@ def _flat(scene: SceneLike) -> FlatScene:
 
 def _opts(precision: str = "f64", max_depth: int = World.MAX_REFLECTION_ITERATIONS, n_gpus: int = 1, band_rows: int = 16,
           family: Optional[str] = None) -> abi.RtgpuOpts:
-    """family: None (library default / RTGPU_WAVEFRONT), "wavefront" or "persistent" (include/rtgpu.h RTGPU_FLAG_*)."""
+    """family: None (auto: RTGPU_FAMILY, else the library times both and keeps the faster), "wavefront" or
+    "persistent" (include/rtgpu.h RTGPU_FLAG_*)."""
     prec = {"f64": abi.PRECISION_F64, "f32": abi.PRECISION_F32}[precision]
     flags = {None: 0, "wavefront": abi.FLAG_WAVEFRONT, "persistent": abi.FLAG_PERSISTENT}[family]
     return abi.RtgpuOpts(prec, int(max_depth), int(n_gpus), int(band_rows), flags)
+
+
+FAMILY_NAMES = ("persistent", "wavefront")
+
+
+def last_family() -> str:
+    """The kernel family this thread's most recent render ran (``rtgpu_last_family``)."""
+    return FAMILY_NAMES[int(abi.load_library().rtgpu_last_family())]
 
 
 def device_count() -> int:
@@ -70,7 +79,7 @@ def render_gpu(
     abi.check(lib, st)
     canvas = Canvas(camera.horizontal_size, camera.vertical_size, rgb if rgb is not None else np.zeros((n, 3)), rgb8)
     if return_stats:
-        return canvas, stats.as_dict()
+        return canvas, dict(stats.as_dict(), family=last_family())
     return canvas
 
 
@@ -141,7 +150,7 @@ class Renderer:
             C.byref(stats),
         )
         abi.check(self._lib, st)
-        return out_rgb, out_rgb8, stats.as_dict()
+        return out_rgb, out_rgb8, dict(stats.as_dict(), family=last_family())
 
     def render_device(
         self,

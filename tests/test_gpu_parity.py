@@ -326,3 +326,27 @@ def test_wavefront_shards_and_synthetic():
     from ray_tracer_challenge_rs_b200.synthetic import synthetic_camera, synthetic_scene
 
     compare_with_oracle(synthetic_scene(3000, extent=9.0), synthetic_camera(192, 108, distance=23.4), label="wavefront:synthetic3000", family="wavefront")
+
+
+def test_auto_family_measures_then_settles(monkeypatch):
+    """family=None: a context times two frames of each family (P, W, P, W), then keeps one; every frame is the
+    same bits whichever family rendered it.  Scenes without reflective / transparent materials never leave the
+    persistent kernel."""
+    monkeypatch.delenv("RTGPU_FAMILY", raising=False)
+    monkeypatch.delenv("RTGPU_WAVEFRONT", raising=False)
+    flat, camera = load_scene_fixture("cover")
+    cam = camera.resized(320, 180)
+    with Renderer(flat) as r:
+        frames = [r.render(cam) for _ in range(8)]
+        other = [r.render(cam.resized(160, 90))[2]["family"] for _ in range(2)]  # another frame shape: measured afresh
+    families = [st["family"] for _, _, st in frames]
+    assert families[:4] == ["persistent", "wavefront", "persistent", "wavefront"], families
+    assert len(set(families[4:])) == 1, families
+    assert other == ["persistent", "wavefront"], other
+    for rgb, rgb8, st in frames[1:]:
+        assert np.array_equal(rgb.view(np.uint64), frames[0][0].view(np.uint64))
+        assert np.array_equal(rgb8, frames[0][1])
+        assert {k: st[k] for k in COUNTERS} == {k: frames[0][2][k] for k in COUNTERS}
+    flat, camera = load_scene_fixture("three_sphere_scene")
+    with Renderer(flat) as r:
+        assert [r.render(camera.resized(160, 80))[2]["family"] for _ in range(5)] == ["persistent"] * 5
