@@ -180,7 +180,7 @@ def run_reference(args):
     mrays = stats["rays"] * len(times) / total / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic: the reference's cover scene (committed flattened fixture), camera resized",
         "config": workload_config(args, flat),
         "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port",
@@ -190,13 +190,14 @@ def run_reference(args):
         "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "rays_per_frame": stats["rays"],
     }
-    print(json.dumps(line))
+    RESULT_LINE.append(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 
 
+RESULT_LINE = []  # filled by the arm that ran; printed by main() once stdout is back
 CALIBRATION_FRAMES = 4  # 2 per kernel family (TUNE_RUNS in csrc/rtgpu.cu)
 
 
@@ -370,7 +371,7 @@ def run_b200(args):
             "rays_per_frame": rays, "ms_per_frame": device_ms / K, "wall_ms_per_step_incl_flush": (t_wall1 - t_wall0) * 1e3 / K,
             "counters": stats,
         }
-        print(json.dumps(line))
+        RESULT_LINE.append(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -390,10 +391,22 @@ def main():
                     help="kernel family; auto = the library measures both on the first frames and keeps the faster")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    # stdout carries exactly one JSON line: anything libraries print to fd 1 on the way (NCCL's version banner,
+    # torchrun notices) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if RESULT_LINE:
+        print(RESULT_LINE[0], flush=True)
 
 
 if __name__ == "__main__":

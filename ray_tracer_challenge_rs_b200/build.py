@@ -17,7 +17,7 @@ INCLUDE = os.path.join(os.path.dirname(PACKAGE_DIR), "include")
 OUTPUT = os.path.join(PACKAGE_DIR, "librtgpu.so")
 
 SOURCES = ["rtgpu.cu"]
-HEADERS = ["rt_kernel.cuh", "rt_scene.h"]
+HEADERS = ["rt_kernel.cuh", "rt_wavefront.cuh", "rt_arith.cuh", "rt_bvh.h", "rt_scene.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

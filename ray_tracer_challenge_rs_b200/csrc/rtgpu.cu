@@ -15,6 +15,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rtgpu.h"
@@ -1321,27 +1322,51 @@ int rtgpu_render(const rtgpu_scene* scene, const rtgpu_camera* camera, const rtg
             }
             cache[g] = ctx;
         }
-        CUDA_TRY(cudaSetDevice(g));
-        st = upload_scene(cache[g], packed);
-        if (st != RTGPU_OK) return st;
     }
-    // row bands: device g renders bands g, g+G, g+2G, ... (interleaved: per-row cost varies a lot)
-    for (int g = 0; g < n_gpus; ++g) {
+    // row bands: device g renders bands g, g+G, g+2G, ... (interleaved: per-row cost varies a lot).
+    // One host thread per device (the caller's for device 0): upload, launches, copies and the final wait of the
+    // devices proceed side by side instead of queueing behind one another on a single submitting thread.
+    struct DeviceJob {
+        int status = RTGPU_OK;
+        std::string error;
+        rtgpu_stats stats{};
+    };
+    std::vector<DeviceJob> jobs(n_gpus);
+    auto work = [&](int g) {
+        DeviceJob& job = jobs[g];
         rtgpu_rows rows;
         rows.band_rows = n_gpus == 1 ? 0u : band_rows;
         rows.shard_index = (uint32_t)g;
         rows.shard_count = (uint32_t)n_gpus;
-        st = enqueue_host_render(cache[g], camera, opts, &rows, out_rgb, out_rgb8);
-        if (st != RTGPU_OK) return st;
+        int rc = cudaSetDevice(g) == cudaSuccess ? RTGPU_OK : fail(RTGPU_ERR_CUDA, "cudaSetDevice(%d) failed", g);
+        if (rc == RTGPU_OK) rc = upload_scene(cache[g], packed);
+        if (rc == RTGPU_OK) rc = enqueue_host_render(cache[g], camera, opts, &rows, out_rgb, out_rgb8);
+        if (rc == RTGPU_OK) rc = finish_host_render(cache[g], camera, opts, &rows, out_rgb, out_rgb8, stats ? &job.stats : nullptr);
+        job.status = rc;
+        if (rc != RTGPU_OK) job.error = g_last_error;
+    };
+    {
+        std::vector<std::thread> helpers;
+        for (int g = 1; g < n_gpus; ++g) helpers.emplace_back(work, g);
+        work(0);
+        for (auto& t : helpers) t.join();
     }
     for (int g = 0; g < n_gpus; ++g) {
-        rtgpu_rows rows;
-        rows.band_rows = n_gpus == 1 ? 0u : band_rows;
-        rows.shard_index = (uint32_t)g;
-        rows.shard_count = (uint32_t)n_gpus;
-        st = finish_host_render(cache[g], camera, opts, &rows, out_rgb, out_rgb8, stats);
-        if (st != RTGPU_OK) return st;
+        if (jobs[g].status != RTGPU_OK) {
+            g_last_error = jobs[g].error;
+            return jobs[g].status;
+        }
+        if (stats) {
+            stats->rays_primary += jobs[g].stats.rays_primary;
+            stats->rays_shadow += jobs[g].stats.rays_shadow;
+            stats->rays_reflect += jobs[g].stats.rays_reflect;
+            stats->rays_refract += jobs[g].stats.rays_refract;
+            stats->hit_nodes += jobs[g].stats.hit_nodes;
+            stats->pixels += jobs[g].stats.pixels;
+            stats->kernel_ms = std::max(stats->kernel_ms, jobs[g].stats.kernel_ms);
+        }
     }
+    g_last_family = cache[0]->last_family;
     if (stats) stats->total_ms = wall_ms() - t0;
     return RTGPU_OK;
 }
