@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--shapes", type=int, nargs="+", default=[10000, 100000, 1000000])
     ap.add_argument("--width", type=int, default=7680)
     ap.add_argument("--height", type=int, default=4320)
-    ap.add_argument("--frames", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=5)
     ap.add_argument("--sample", type=int, default=512, help="pixels checked against the CPU oracle")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()

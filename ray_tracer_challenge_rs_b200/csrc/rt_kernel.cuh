@@ -32,6 +32,12 @@
 
 namespace rt {
 
+#ifndef RT_ACC_SPLIT
+#define RT_ACC_SPLIT 1
+#endif
+#ifndef RT_BVH_WATCHDOG
+#define RT_BVH_WATCHDOG 0
+#endif
 #ifndef RT_CULL
 #define RT_CULL 1  // bounding-sphere pre-test in the intersection loop (exact results either way)
 #endif
@@ -166,23 +172,87 @@ template <typename T> RT_DEV V3<T> mat_transposed_vector(const T* m, V3<T> v) {
 
 // ---------------------------------------------------------------------------------------------
 // The scene as the kernel sees it (shared memory when it fits, else global).
-template <typename T>
+// SMEM = true: both blobs were staged at the start of dynamic shared memory (stage_scene): the accessors name
+// that array directly, so every table read is an LDS with a uniform base.  Going through pointer members
+// instead cost generic LD.E loads — the view's address escapes to the out-of-line helpers, so ptxas cannot
+// tell which window the pointers refer to (measured: -5..14 % frame time on the persistent family).
+// SMEM = false: the blobs are read from global memory through L1 / L2.
+template <typename T, bool SMEM>
 struct SceneView {
     const T* reals;
     const int* ints;
     SceneLayout L;
-    RT_DEV const T* shape(uint32_t pos) const { return reals + (size_t)pos * SHAPE_REALS; }
-    RT_DEV int4 shape_meta(uint32_t pos) const { return reinterpret_cast<const int4*>(ints)[(size_t)pos * (SHAPE_INTS / 4)]; }
-    RT_DEV const T* triangle(uint32_t pos) const { return reals + L.tri_off + (size_t)ints[(size_t)pos * SHAPE_INTS + 4] * TRI_REALS; }
-    RT_DEV const T* bvh_boxes(uint32_t node) const { return reals + L.bvh_off + (size_t)node * BVH_REALS; }
-    RT_DEV int2 bvh_children(uint32_t node) const { return reinterpret_cast<const int2*>(ints + L.bvh_meta_off)[node]; }
-    RT_DEV const T* material(uint32_t m) const { return reals + L.mat_off + (size_t)m * MAT_REALS; }
-    RT_DEV int material_pattern(uint32_t m) const { return ints[L.mat_meta_off + m * MAT_INTS]; }
-    RT_DEV const T* pattern(uint32_t p) const { return reals + L.pat_off + (size_t)p * PAT_REALS; }
-    RT_DEV const int* pattern_meta(uint32_t p) const { return ints + L.pat_meta_off + p * PAT_INTS; }
-    RT_DEV const T* light(uint32_t l) const { return reals + L.light_off + (size_t)l * LIGHT_REALS; }
-    RT_DEV const T* cull(uint32_t pos) const { return reals + L.cull_off + (size_t)pos * CULL_REALS; }
+    RT_DEV const T* R() const {
+        if constexpr (SMEM) {
+            extern __shared__ __align__(16) unsigned char rt_scene_smem[];
+            return reinterpret_cast<const T*>(rt_scene_smem);
+        } else {
+            return reals;
+        }
+    }
+    RT_DEV const int* I() const {
+        if constexpr (SMEM) {
+            extern __shared__ __align__(16) unsigned char rt_scene_smem[];
+            return reinterpret_cast<const int*>(rt_scene_smem + (((size_t)L.n_reals * sizeof(T) + 15) & ~size_t(15)));
+        } else {
+            return ints;
+        }
+    }
+    RT_DEV const T* shape(uint32_t pos) const { return R() + (size_t)pos * SHAPE_REALS; }
+    RT_DEV int4 shape_meta(uint32_t pos) const { return reinterpret_cast<const int4*>(I())[(size_t)pos * (SHAPE_INTS / 4)]; }
+    RT_DEV const T* triangle(uint32_t pos) const { return R() + L.tri_off + (size_t)I()[(size_t)pos * SHAPE_INTS + 4] * TRI_REALS; }
+    RT_DEV const T* bvh_boxes(uint32_t node) const { return R() + L.bvh_off + (size_t)node * BVH_REALS; }
+    RT_DEV int2 bvh_children(uint32_t node) const { return reinterpret_cast<const int2*>(I() + L.bvh_meta_off)[node]; }
+    RT_DEV const T* material(uint32_t m) const { return R() + L.mat_off + (size_t)m * MAT_REALS; }
+    RT_DEV int material_pattern(uint32_t m) const { return I()[L.mat_meta_off + m * MAT_INTS]; }
+    RT_DEV const T* pattern(uint32_t p) const { return R() + L.pat_off + (size_t)p * PAT_REALS; }
+    RT_DEV const int* pattern_meta(uint32_t p) const { return I() + L.pat_meta_off + p * PAT_INTS; }
+    RT_DEV const T* light(uint32_t l) const { return R() + L.light_off + (size_t)l * LIGHT_REALS; }
+    RT_DEV const T* cull(uint32_t pos) const { return R() + L.cull_off + (size_t)pos * CULL_REALS; }
 };
+
+// Copy both scene blobs to the start of dynamic shared memory with the TMA unit: two bulk asynchronous copies
+// (cp.async.bulk, SASS UBLKCP) issued by one thread, completion counted in bytes on an mbarrier that every
+// thread then waits on.  The packer pads both blobs to multiples of 16 bytes; cudaMalloc and the shared window
+// are aligned.  Called by every thread of the CTA, once, before anything else touches shared memory.
+template <typename T>
+RT_DEV void stage_scene(const SceneLayout& layout, const T* __restrict__ g_reals, const int* __restrict__ g_ints) {
+    extern __shared__ __align__(16) unsigned char rt_scene_smem[];
+    T* s_reals = reinterpret_cast<T*>(rt_scene_smem);
+    int* s_ints = reinterpret_cast<int*>(rt_scene_smem + (((size_t)layout.n_reals * sizeof(T) + 15) & ~size_t(15)));
+#if RT_TMA_STAGE
+    __shared__ __align__(8) unsigned long long stage_bar;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&stage_bar);
+    const uint32_t bytes_reals = layout.n_reals * (uint32_t)sizeof(T), bytes_ints = layout.n_ints * (uint32_t)sizeof(int);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes_reals + bytes_ints) : "memory");
+        if (bytes_reals)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(s_reals)),
+                         "l"(g_reals), "r"(bytes_reals), "r"(bar)
+                         : "memory");
+        if (bytes_ints)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(s_ints)),
+                         "l"(g_ints), "r"(bytes_ints), "r"(bar)
+                         : "memory");
+    }
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
+    }
+#else
+    for (uint32_t i = threadIdx.x; i < layout.n_reals; i += blockDim.x) s_reals[i] = g_reals[i];
+    for (uint32_t i = threadIdx.x; i < layout.n_ints; i += blockDim.x) s_ints[i] = g_ints[i];
+    __syncthreads();
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------
 // What one trace accumulates.  Three query kinds share the intersection loop:
@@ -216,8 +286,21 @@ struct TraceAcc {
     T best_t;       // RADIANCE: +max seed; SHADOW: light distance seed
     int best_orig;  // world order of the best hit (tie-break), INT_MAX seed
     int best_pos;   // sorted position of the best hit, -1 = none
-    ContainerAcc<T> c;
+    ContainerAcc<T>* c;  // a separate object: its address escapes to the out-of-line consume_container, and the
+                         // hot fields above must stay promotable to registers
+#if !RT_ACC_SPLIT
+    ContainerAcc<T> c_store;  // A/B: c points here, the whole accumulator escapes and lives in local memory
+#endif
 };
+
+template <typename T>
+RT_DEV ContainerAcc<T>* acc_store(TraceAcc<T>& a) {
+#if RT_ACC_SPLIT
+    return nullptr;
+#else
+    return &a.c_store;
+#endif
+}
 
 // The container query's bookkeeping for one shape (rare: only hits on transparent materials ask for
 // it), kept out of line so the three hot query loops stay small.
@@ -272,7 +355,7 @@ RT_DEV void consume(TraceAcc<T>& a, int n, T t0, T t1, T t2, T t3, int pos, int4
             }
         }
     } else if (meta.z & FLAG_CONTAINER_REP) {
-        consume_container(a.c, n, t0, t1, t2, t3, pos, meta);
+        consume_container(*a.c, n, t0, t1, t2, t3, pos, meta);
     }
 }
 
@@ -487,8 +570,8 @@ RT_DEV int local_intersect(const Ray<T>& r, const T* g, int flags, const T* tri,
 
 // Ray::intersect (ray.rs:35-49) for the shape at sorted position `pos`, of (compile-time) type TYPE:
 // object-space ray, local_intersect, then the query's bookkeeping.
-template <typename T, int TYPE>
-RT_DEV void test_shape(const SceneView<T>& sv, uint32_t pos, const Ray<T>& ray, TraceAcc<T>& acc) {
+template <typename T, int TYPE, bool SMEM>
+RT_DEV void test_shape(const SceneView<T, SMEM>& sv, uint32_t pos, const Ray<T>& ray, TraceAcc<T>& acc) {
     const T* g = sv.shape(pos);
     int4 meta = sv.shape_meta(pos);
     Ray<T> local;
@@ -501,8 +584,8 @@ RT_DEV void test_shape(const SceneView<T>& sv, uint32_t pos, const Ray<T>& ray, 
 }
 
 // World::collect_intersections (world.rs:25-35) over the flat per-type lists: every shape, no dispatch.
-template <typename T, int TYPE>
-RT_DEV void trace_type(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
+template <typename T, int TYPE, bool SMEM>
+RT_DEV void trace_type(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
     const uint32_t b = sv.L.type_begin[TYPE], e = sv.L.type_begin[TYPE + 1];
     for (uint32_t pos = b; pos < e; ++pos) {
 #if RT_CULL
@@ -548,8 +631,8 @@ RT_DEV bool box_hit(const T* b, const Ray<T>& ray, V3<T> inv, T t_lo, T t_hi, T&
     return tn <= tf;
 }
 
-template <typename T, bool FULL>
-RT_DEV void trace_bvh(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
+template <typename T, bool FULL, bool SMEM>
+RT_DEV void trace_bvh(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
     const bool active = acc.mode != MODE_IDLE;
     // 1 / d per axis; only used for the conservative box tests, so plain reciprocals are enough.
     // A zero component gives +-inf, which the slab test handles.
@@ -559,8 +642,24 @@ RT_DEV void trace_bvh(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& ac
     int sp = 0;
     int cur = active ? 0 : INT_MIN;  // INT_MIN = nothing left to visit; >= 0 inner node; < 0 leaf ~pos
     int pending = -1;                // leaf waiting for its exact test
+#if RT_BVH_WATCHDOG
+    unsigned long long wd_outer = 0, wd_inner = 0;
+#endif
     for (;;) {
+#if RT_BVH_WATCHDOG
+        if (++wd_outer > 2000000ull) {
+            printf("bvh watchdog outer: blk %d thr %d mode %d cur %d pending %d sp %d best_t %g inner %llu\n", blockIdx.x, threadIdx.x, acc.mode, cur, pending, sp, (double)acc.best_t, wd_inner);
+            break;
+        }
+#endif
         while (pending < 0 && cur != INT_MIN) {
+#if RT_BVH_WATCHDOG
+            if (++wd_inner > 4000000ull) {
+                printf("bvh watchdog inner: blk %d thr %d mode %d cur %d sp %d\n", blockIdx.x, threadIdx.x, acc.mode, cur, sp);
+                cur = INT_MIN;
+                break;
+            }
+#endif
             if (cur < 0) {
                 pending = ~cur;
                 cur = sp > 0 ? stack[--sp] : INT_MIN;
@@ -568,7 +667,7 @@ RT_DEV void trace_bvh(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& ac
             }
             const T* nb = sv.bvh_boxes((uint32_t)cur);
             const int2 ch = sv.bvh_children((uint32_t)cur);
-            const T t_hi = (acc.mode == MODE_CONTAINER) ? acc.c.t_hit : acc.best_t;
+            const T t_hi = (acc.mode == MODE_CONTAINER) ? acc.c->t_hit : acc.best_t;
             T e0, e1;
             const bool h0 = box_hit(nb, ray, inv, t_lo, t_hi, e0);
             const bool h1 = box_hit(nb + 6, ray, inv, t_lo, t_hi, e1);
@@ -582,16 +681,21 @@ RT_DEV void trace_bvh(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& ac
                 cur = sp > 0 ? stack[--sp] : INT_MIN;
             }
         }
-        // exact tests, one shape type at a time across the warp
-        unsigned waiting = __ballot_sync(0xffffffffu, pending >= 0);
+        // exact tests, one shape type at a time across the lanes that walk together.  `group` is whoever is
+        // converged here — after the divergent loop above that is normally the whole warp.  Voting on the full
+        // mask instead is legal CUDA but deadlocked in one build of the wavefront kernel (10^4 shapes at 1080p,
+        // level-0 launch never finished; adding a printf to the loop made it go away): with the group's own mask
+        // no lane ever waits for a lane outside its convergence group, whatever ptxas does with the barriers.
+        const unsigned group = __activemask();
+        unsigned waiting = __ballot_sync(group, pending >= 0);
         if (waiting == 0u) {
-            if (__all_sync(0xffffffffu, cur == INT_MIN)) break;
+            if (__all_sync(group, cur == INT_MIN)) break;
             continue;
         }
         const int my_type = pending >= 0 ? ((sv.shape_meta((uint32_t)pending).z >> FLAG_TYPE_SHIFT) & 7) : -1;
         while (waiting) {
             const int leader = __ffs(waiting) - 1;
-            const int type = __shfl_sync(0xffffffffu, my_type, leader);
+            const int type = __shfl_sync(group, my_type, leader);
             if (pending >= 0 && my_type == type) {
                 switch (type) {
                 case 0: test_shape<T, 0>(sv, (uint32_t)pending, ray, acc); break;
@@ -608,7 +712,7 @@ RT_DEV void trace_bvh(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& ac
                     sp = 0;
                 }
             }
-            waiting = __ballot_sync(0xffffffffu, pending >= 0);
+            waiting = __ballot_sync(group, pending >= 0);
         }
     }
 }
@@ -617,8 +721,8 @@ RT_DEV void trace_bvh(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& ac
 // object-space transform and the query bookkeeping exist ONCE in the instruction stream instead of once
 // per shape type.  The render kernel is bound by instruction-cache misses (GCC request rate), so code
 // bytes on the hot path matter more than the handful of extra instructions per shape.
-template <typename T, bool FULL>
-RT_DEV void trace_unified(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
+template <typename T, bool FULL, bool SMEM>
+RT_DEV void trace_unified(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
     const uint32_t n = sv.L.type_begin[NUM_SHAPE_TYPES];
     for (uint32_t pos = 0; pos < n; ++pos) {
 #if RT_CULL
@@ -652,8 +756,8 @@ RT_DEV void trace_unified(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>
 
 // FULL = false: the scene holds only spheres, planes and cubes (all but one shipped scene); the
 // cylinder / cone / triangle loops are not even instantiated, which keeps the code footprint down.
-template <typename T, bool FULL>
-RT_DEV void trace(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
+template <typename T, bool FULL, bool SMEM>
+RT_DEV void trace(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
     trace_type<T, 0>(sv, ray, acc);
     trace_type<T, 1>(sv, ray, acc);
     trace_type<T, 2>(sv, ray, acc);
@@ -670,8 +774,8 @@ template <typename T> RT_DEV bool coarse_eq(T a, T b) { return a == b || fabs(a 
 
 // local_normal_at of the six shapes (sphere.rs:57-59, plane.rs:52-54, cube.rs:89-101,
 // cylinder.rs:114-126, cone.rs:116-133, triangle.rs:78-80)
-template <typename T>
-RT_COLD V3<T> local_normal_at(const SceneView<T>& sv, uint32_t pos, int type, const T* g, V3<T> p) {
+template <typename T, bool SMEM>
+RT_COLD V3<T> local_normal_at(const SceneView<T, SMEM>& sv, uint32_t pos, int type, const T* g, V3<T> p) {
     switch (type) {
     case 0: return p;
     case 1: return mk<T>(T(0), T(1), T(0));
@@ -710,8 +814,8 @@ RT_COLD bool even_as_i64(T v) {
 }
 
 // Pattern::color_at (patterns/*.rs) at pattern-space point p
-template <typename T>
-RT_COLD V3<T> pattern_color_at(const SceneView<T>& sv, int pattern, V3<T> p) {
+template <typename T, bool SMEM>
+RT_COLD V3<T> pattern_color_at(const SceneView<T, SMEM>& sv, int pattern, V3<T> p) {
     for (;;) {
         const T* pr = sv.pattern(pattern);
         const int* pm = sv.pattern_meta(pattern);
@@ -780,58 +884,16 @@ constexpr int TILE_W = 8, TILE_H = 4;   // a warp's 32 pixel slots = one 8x4 til
 #endif
 constexpr int CHUNK_SLOTS = RT_CHUNK_SLOTS;  // slots a warp takes from the global counter at a time
 
-template <typename T, int MAX_FRAMES, bool FULL, bool BVH>
+template <typename T, int MAX_FRAMES, bool FULL, bool BVH, bool SMEM>
 __global__ void __launch_bounds__(RT_BLOCK_THREADS, RT_MIN_BLOCKS_PER_SM)
 render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, SceneLayout layout, CameraParams<T> cam,
               T* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8, unsigned long long* __restrict__ counters,
               unsigned int* __restrict__ work_counter) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SceneView<T> sv;
+    SceneView<T, SMEM> sv;
     sv.L = layout;
-    if (layout.in_shared) {
-        T* s_reals = reinterpret_cast<T*>(smem_raw);
-        int* s_ints = reinterpret_cast<int*>(smem_raw + (((size_t)layout.n_reals * sizeof(T) + 15) & ~size_t(15)));
-#if RT_TMA_STAGE
-        // Stage both scene blobs with the TMA unit: two bulk asynchronous copies (cp.async.bulk, SASS UBLKCP)
-        // issued by one thread, completion counted in bytes on an mbarrier that every thread then waits on.
-        // The packer pads both blobs to multiples of 16 bytes, and cudaMalloc / the shared window are aligned.
-        __shared__ __align__(8) unsigned long long stage_bar;
-        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&stage_bar);
-        const uint32_t bytes_reals = layout.n_reals * (uint32_t)sizeof(T), bytes_ints = layout.n_ints * (uint32_t)sizeof(int);
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes_reals + bytes_ints) : "memory");
-            if (bytes_reals)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 (uint32_t)__cvta_generic_to_shared(s_reals)),
-                             "l"(g_reals), "r"(bytes_reals), "r"(bar)
-                             : "memory");
-            if (bytes_ints)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 (uint32_t)__cvta_generic_to_shared(s_ints)),
-                             "l"(g_ints), "r"(bytes_ints), "r"(bar)
-                             : "memory");
-        }
-        {
-            uint32_t done = 0;
-            while (!done)
-                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
-        }
-#else
-        for (uint32_t i = threadIdx.x; i < layout.n_reals; i += blockDim.x) s_reals[i] = g_reals[i];
-        for (uint32_t i = threadIdx.x; i < layout.n_ints; i += blockDim.x) s_ints[i] = g_ints[i];
-        __syncthreads();
-#endif
-        sv.reals = s_reals;
-        sv.ints = s_ints;
-    } else {
-        sv.reals = g_reals;
-        sv.ints = g_ints;
-    }
+    sv.reals = g_reals;
+    sv.ints = g_ints;
+    if constexpr (SMEM) stage_scene<T>(layout, g_reals, g_ints);
 
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t tiles_x = (cam.hsize + TILE_W - 1) / TILE_W;
@@ -944,17 +1006,19 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
 
         // ---- phase B: one trace for every lane that has a ray ----------------------------------------
         TraceAcc<T> acc;
+        ContainerAcc<T> cacc;
+        acc.c = RT_ACC_SPLIT ? &cacc : acc_store(acc);
         acc.mode = (state == ST_RADIANCE) ? MODE_RADIANCE : (state == ST_SHADOW) ? MODE_SHADOW : (state == ST_CONTAINER) ? MODE_CONTAINER : MODE_IDLE;
         acc.best_t = (state == ST_SHADOW) ? shadow_distance : Real<T>::max();
         acc.dir_sq = fma(ray.d.z, ray.d.z, fma(ray.d.y, ray.d.y, ray.d.x * ray.d.x));
         acc.best_orig = 0x7fffffff;
         acc.best_pos = -1;
-        acc.c.t_hit = t_hit;
-        acc.c.hit_class = (state == ST_CONTAINER) ? sv.shape_meta((uint32_t)hit_pos).w : -1;
-        acc.c.hit_class_inside = false;
-        acc.c.all_pos = acc.c.excl_pos = -1;
-        acc.c.all_t = acc.c.excl_t = T(0);
-        acc.c.all_orig = acc.c.excl_orig = 0;
+        acc.c->t_hit = t_hit;
+        acc.c->hit_class = (state == ST_CONTAINER) ? sv.shape_meta((uint32_t)hit_pos).w : -1;
+        acc.c->hit_class_inside = false;
+        acc.c->all_pos = acc.c->excl_pos = -1;
+        acc.c->all_t = acc.c->excl_t = T(0);
+        acc.c->all_orig = acc.c->excl_orig = 0;
 #if RT_UNIFIED_LOOP
         if (acc.mode != MODE_IDLE) trace_unified<T, FULL>(sv, ray, acc);  // uniform list (BVH scenes: the unbounded shapes)
 #else
@@ -1004,9 +1068,9 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
         } else if (state == ST_CONTAINER) {
             // intersection.rs:33-62
             const int hit_mat = hit_material;
-            n1 = (acc.c.all_pos >= 0) ? sv.material((uint32_t)sv.shape_meta((uint32_t)acc.c.all_pos).y)[MAT_REFRACTIVE_INDEX] : T(1);
-            if (acc.c.hit_class_inside)
-                n2 = (acc.c.excl_pos >= 0) ? sv.material((uint32_t)sv.shape_meta((uint32_t)acc.c.excl_pos).y)[MAT_REFRACTIVE_INDEX] : T(1);
+            n1 = (acc.c->all_pos >= 0) ? sv.material((uint32_t)sv.shape_meta((uint32_t)acc.c->all_pos).y)[MAT_REFRACTIVE_INDEX] : T(1);
+            if (acc.c->hit_class_inside)
+                n2 = (acc.c->excl_pos >= 0) ? sv.material((uint32_t)sv.shape_meta((uint32_t)acc.c->excl_pos).y)[MAT_REFRACTIVE_INDEX] : T(1);
             else
                 n2 = sv.material((uint32_t)hit_mat)[MAT_REFRACTIVE_INDEX];
             finish_hit = true;

@@ -107,16 +107,16 @@ RT_DEV void wf_reset_acc(TraceAcc<T>& acc, int mode, const Ray<T>& ray, T best_t
     acc.dir_sq = fma(ray.d.z, ray.d.z, fma(ray.d.y, ray.d.y, ray.d.x * ray.d.x));
     acc.best_orig = 0x7fffffff;
     acc.best_pos = -1;
-    acc.c.t_hit = T(0);
-    acc.c.hit_class = -1;
-    acc.c.hit_class_inside = false;
-    acc.c.all_pos = acc.c.excl_pos = -1;
-    acc.c.all_t = acc.c.excl_t = T(0);
-    acc.c.all_orig = acc.c.excl_orig = 0;
+    acc.c->t_hit = T(0);
+    acc.c->hit_class = -1;
+    acc.c->hit_class_inside = false;
+    acc.c->all_pos = acc.c->excl_pos = -1;
+    acc.c->all_t = acc.c->excl_t = T(0);
+    acc.c->all_orig = acc.c->excl_orig = 0;
 }
 
-template <typename T, bool FULL, bool BVH>
-RT_DEV void wf_trace(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
+template <typename T, bool FULL, bool BVH, bool SMEM>
+RT_DEV void wf_trace(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
 #if RT_UNIFIED_LOOP
     if (acc.mode != MODE_IDLE) trace_unified<T, FULL>(sv, ray, acc);
 #else
@@ -125,51 +125,17 @@ RT_DEV void wf_trace(const SceneView<T>& sv, const Ray<T>& ray, TraceAcc<T>& acc
     if (BVH) trace_bvh<T, FULL>(sv, ray, acc);  // warp votes inside: every lane takes part
 }
 
-template <typename T, bool FULL, bool BVH>
+template <typename T, bool FULL, bool BVH, bool SMEM>
 __global__ void __launch_bounds__(RT_WF_THREADS, RT_WF_MIN_BLOCKS)
 wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, SceneLayout layout, CameraParams<T> cam, int level,
                 const WfRay<T>* __restrict__ rays_in, WfRay<T>* __restrict__ rays_out, unsigned cap_rays, WfNode<T>* __restrict__ nodes,
                 unsigned cap_nodes, WfCounts* __restrict__ counts, T* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8,
                 unsigned long long* __restrict__ counters) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SceneView<T> sv;
+    SceneView<T, SMEM> sv;
     sv.L = layout;
-    if (layout.in_shared) {
-        T* s_reals = reinterpret_cast<T*>(smem_raw);
-        int* s_ints = reinterpret_cast<int*>(smem_raw + (((size_t)layout.n_reals * sizeof(T) + 15) & ~size_t(15)));
-        // cp.async.bulk + mbarrier staging, as in render_kernel
-        __shared__ __align__(8) unsigned long long stage_bar;
-        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&stage_bar);
-        const uint32_t bytes_reals = layout.n_reals * (uint32_t)sizeof(T), bytes_ints = layout.n_ints * (uint32_t)sizeof(int);
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes_reals + bytes_ints) : "memory");
-            if (bytes_reals)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 (uint32_t)__cvta_generic_to_shared(s_reals)),
-                             "l"(g_reals), "r"(bytes_reals), "r"(bar)
-                             : "memory");
-            if (bytes_ints)
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 (uint32_t)__cvta_generic_to_shared(s_ints)),
-                             "l"(g_ints), "r"(bytes_ints), "r"(bar)
-                             : "memory");
-        }
-        {
-            uint32_t done = 0;
-            while (!done)
-                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar) : "memory");
-        }
-        sv.reals = s_reals;
-        sv.ints = s_ints;
-    } else {
-        sv.reals = g_reals;
-        sv.ints = g_ints;
-    }
+    sv.reals = g_reals;
+    sv.ints = g_ints;
+    if constexpr (SMEM) stage_scene<T>(layout, g_reals, g_ints);
 
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t tiles_x = (cam.hsize + TILE_W - 1) / TILE_W;
@@ -306,10 +272,12 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
             }
 
             TraceAcc<T> acc;
+            ContainerAcc<T> cacc;
+            acc.c = RT_ACC_SPLIT ? &cacc : acc_store(acc);
             wf_reset_acc(acc, mode, tray, seed);
             if (phase == 1 && need_containers) {
-                acc.c.t_hit = t_hit;
-                acc.c.hit_class = sv.shape_meta((uint32_t)hit_pos).w;
+                acc.c->t_hit = t_hit;
+                acc.c->hit_class = sv.shape_meta((uint32_t)hit_pos).w;
             }
             if (__any_sync(0xffffffffu, mode != MODE_IDLE)) wf_trace<T, FULL, BVH>(sv, tray, acc);
 
@@ -345,9 +313,9 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                 // ---- n1 / n2 (intersection.rs:39-58), children to spawn, Schlick, base colour --------------
                 T n1 = T(1), n2 = T(1);  // Material::DEFAULT_REFRACTIVE_INDEX
                 if (need_containers) {
-                    n1 = (acc.c.all_pos >= 0) ? sv.material((uint32_t)sv.shape_meta((uint32_t)acc.c.all_pos).y)[MAT_REFRACTIVE_INDEX] : T(1);
-                    if (acc.c.hit_class_inside)
-                        n2 = (acc.c.excl_pos >= 0) ? sv.material((uint32_t)sv.shape_meta((uint32_t)acc.c.excl_pos).y)[MAT_REFRACTIVE_INDEX] : T(1);
+                    n1 = (acc.c->all_pos >= 0) ? sv.material((uint32_t)sv.shape_meta((uint32_t)acc.c->all_pos).y)[MAT_REFRACTIVE_INDEX] : T(1);
+                    if (acc.c->hit_class_inside)
+                        n2 = (acc.c->excl_pos >= 0) ? sv.material((uint32_t)sv.shape_meta((uint32_t)acc.c->excl_pos).y)[MAT_REFRACTIVE_INDEX] : T(1);
                     else
                         n2 = sv.material((uint32_t)hit_material)[MAT_REFRACTIVE_INDEX];
                 }

@@ -544,16 +544,23 @@ struct rtgpu_context {
 
 namespace {
 
-template <typename T, int MAX_FRAMES, bool FULL, bool BVH>
+// Bytes of dynamic shared memory the staged scene needs, or 0 when it does not fit the budget that keeps
+// several CTAs resident per SM (then the kernels instantiated with SMEM = false read it from global memory).
+template <typename T>
+size_t scene_smem_bytes(const rtgpu_context* ctx) {
+    const rt::SceneLayout& lay = ctx->layout;
+    const size_t smem = (((size_t)lay.n_reals * sizeof(T) + 15) & ~size_t(15)) + (size_t)lay.n_ints * sizeof(int);
+    const size_t smem_cap = std::min<size_t>(ctx->smem_optin, 64 * 1024);
+    return smem <= smem_cap ? smem : 0;
+}
+
+template <typename T, int MAX_FRAMES, bool FULL, bool BVH, bool SMEM>
 int launch_kernel_impl(rtgpu_context* ctx, const T* d_reals, const rt::CameraParams<T>& cam, T* d_out, uint8_t* d_out8,
                        unsigned long long* d_counters, cudaStream_t stream) {
-    auto kernel = rt::render_kernel<T, MAX_FRAMES, FULL, BVH>;
+    auto kernel = rt::render_kernel<T, MAX_FRAMES, FULL, BVH, SMEM>;
     rt::SceneLayout lay = ctx->layout;
-    size_t smem = (((size_t)lay.n_reals * sizeof(T) + 15) & ~size_t(15)) + (size_t)lay.n_ints * sizeof(int);
-    // keep at least ~3 CTAs of 128 threads per SM resident: stage in shared memory only when small enough
-    const size_t smem_cap = std::min<size_t>(ctx->smem_optin, 64 * 1024);
-    lay.in_shared = smem <= smem_cap ? 1u : 0u;
-    if (!lay.in_shared) smem = 0;
+    const size_t smem = SMEM ? scene_smem_bytes<T>(ctx) : 0;
+    lay.in_shared = SMEM ? 1u : 0u;
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks_per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, RT_BLOCK_THREADS, smem));
@@ -706,15 +713,15 @@ int wavefront_reserve(rtgpu_context* ctx, uint64_t pixels, double growth) {
     return RTGPU_OK;
 }
 
-template <typename T, bool FULL, bool BVH>
+double wall_ms();
+
+template <typename T, bool FULL, bool BVH, bool SMEM>
 int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::CameraParams<T>& cam, T* d_out, uint8_t* d_out8,
                           unsigned long long* d_counters, cudaStream_t stream) {
-    auto level_kernel = rt::wf_level_kernel<T, FULL, BVH>;
+    auto level_kernel = rt::wf_level_kernel<T, FULL, BVH, SMEM>;
     rt::SceneLayout lay = ctx->layout;
-    size_t smem = (((size_t)lay.n_reals * sizeof(T) + 15) & ~size_t(15)) + (size_t)lay.n_ints * sizeof(int);
-    const size_t smem_cap = std::min<size_t>(ctx->smem_optin, 64 * 1024);
-    lay.in_shared = smem <= smem_cap ? 1u : 0u;
-    if (!lay.in_shared) smem = 0;
+    const size_t smem = SMEM ? scene_smem_bytes<T>(ctx) : 0;
+    lay.in_shared = SMEM ? 1u : 0u;
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks_per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, level_kernel, RT_WF_THREADS, smem));
@@ -728,6 +735,11 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
     ctx->wf_cap_nodes = ctx->wf_bytes_nodes / sizeof(rt::WfNode<T>);
     const unsigned grid = (unsigned)(ctx->sm_count * blocks_per_sm);
     const int levels = (int)cam.max_depth + 1;
+    const char* dbg = getenv("RTGPU_DEBUG_SYNC");  // wait after every level and report the queue sizes on stderr
+    const bool debug_sync = dbg && dbg[0] == '1';
+    if (debug_sync)
+        fprintf(stderr, "[rtgpu] wavefront: %llu pixels, grid %u x %d, smem %zu B, queues %zu rays / %zu nodes, FULL %d BVH %d SMEM %d\n",
+                (unsigned long long)pixels, grid, RT_WF_THREADS, smem, ctx->wf_cap_rays, ctx->wf_cap_nodes, (int)FULL, (int)BVH, (int)SMEM);
     if (!ctx->d_wf_counts || !ctx->d_wf_priv || !ctx->d_wf_nodes || !ctx->d_wf_rays[0] || !ctx->d_wf_rays[1])
         return fail(RTGPU_ERR_CUDA, "wavefront buffers missing (counts %p priv %p nodes %p rays %p %p, cap %zu %zu)", (void*)ctx->d_wf_counts,
                     (void*)ctx->d_wf_priv, ctx->d_wf_nodes, ctx->d_wf_rays[0], ctx->d_wf_rays[1], ctx->wf_cap_rays, ctx->wf_cap_nodes);
@@ -743,6 +755,14 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
         CUDA_TRY(cudaGetLastError());
         rt::wf_advance_kernel<<<1, 1, 0, stream>>>(ctx->d_wf_counts, level, (unsigned)ctx->wf_cap_rays);
         CUDA_TRY(cudaGetLastError());
+        if (debug_sync) {
+            const double t0 = wall_ms();
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            rt::WfCounts h;
+            CUDA_TRY(cudaMemcpy(&h, ctx->d_wf_counts, sizeof(h), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[rtgpu] wavefront level %d done (+%.2f ms wait): next queue %u front + %u back, %u nodes, overflow %u\n", level,
+                    wall_ms() - t0, h.n_rays[level + 1], h.n_back[level + 1], h.n_nodes, h.overflow);
+        }
     }
     for (int level = levels - 1; level >= 0; --level)
         rt::wf_combine_kernel<T><<<ctx->sm_count * 4, 256, 0, stream>>>(nodes, ctx->d_wf_counts, level, (unsigned)ctx->wf_cap_nodes, d_out, d_out8);
@@ -754,14 +774,17 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
 template <typename T>
 int launch_wavefront(rtgpu_context* ctx, const T* d_reals, const rt::CameraParams<T>& cam, T* d_out, uint8_t* d_out8,
                      unsigned long long* d_counters, cudaStream_t stream) {
-    const bool full = ctx->has_cyl_cone_tri;
-    const bool bvh = ctx->layout.n_bvh_nodes > 0;
-    if (bvh) {
-        if (full) return launch_wavefront_impl<T, true, true>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
-        return launch_wavefront_impl<T, false, true>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    const int variant = (ctx->has_cyl_cone_tri ? 4 : 0) | (ctx->layout.n_bvh_nodes > 0 ? 2 : 0) | (scene_smem_bytes<T>(ctx) ? 1 : 0);
+    switch (variant) {
+    case 0: return launch_wavefront_impl<T, false, false, false>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    case 1: return launch_wavefront_impl<T, false, false, true>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    case 2: return launch_wavefront_impl<T, false, true, false>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    case 3: return launch_wavefront_impl<T, false, true, true>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    case 4: return launch_wavefront_impl<T, true, false, false>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    case 5: return launch_wavefront_impl<T, true, false, true>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    case 6: return launch_wavefront_impl<T, true, true, false>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    default: return launch_wavefront_impl<T, true, true, true>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
     }
-    if (full) return launch_wavefront_impl<T, true, false>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
-    return launch_wavefront_impl<T, false, false>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
 }
 
 // After a wavefront launch has completed on `stream`: did a queue or the node array overflow?
@@ -787,15 +810,19 @@ int wavefront_check(rtgpu_context* ctx, uint64_t pixels, cudaStream_t stream) {
 template <typename T, int MAX_FRAMES>
 int launch_kernel(rtgpu_context* ctx, const T* d_reals, const rt::CameraParams<T>& cam, T* d_out, uint8_t* d_out8,
                   unsigned long long* d_counters, cudaStream_t stream) {
-    // scenes without cylinders, cones and triangles run the kernel instantiated without those loops
-    const bool full = ctx->has_cyl_cone_tri;
-    const bool bvh = ctx->layout.n_bvh_nodes > 0;
-    if (bvh) {
-        if (full) return launch_kernel_impl<T, MAX_FRAMES, true, true>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
-        return launch_kernel_impl<T, MAX_FRAMES, false, true>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    // scenes without cylinders, cones and triangles run the kernel instantiated without those loops; scenes
+    // below the BVH threshold the one without the traversal; small scenes the one that reads shared memory
+    const int variant = (ctx->has_cyl_cone_tri ? 4 : 0) | (ctx->layout.n_bvh_nodes > 0 ? 2 : 0) | (scene_smem_bytes<T>(ctx) ? 1 : 0);
+    switch (variant) {
+    case 0: return launch_kernel_impl<T, MAX_FRAMES, false, false, false>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    case 1: return launch_kernel_impl<T, MAX_FRAMES, false, false, true>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    case 2: return launch_kernel_impl<T, MAX_FRAMES, false, true, false>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    case 3: return launch_kernel_impl<T, MAX_FRAMES, false, true, true>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    case 4: return launch_kernel_impl<T, MAX_FRAMES, true, false, false>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    case 5: return launch_kernel_impl<T, MAX_FRAMES, true, false, true>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    case 6: return launch_kernel_impl<T, MAX_FRAMES, true, true, false>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
+    default: return launch_kernel_impl<T, MAX_FRAMES, true, true, true>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
     }
-    if (full) return launch_kernel_impl<T, MAX_FRAMES, true, false>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
-    return launch_kernel_impl<T, MAX_FRAMES, false, false>(ctx, d_reals, cam, d_out, d_out8, d_counters, stream);
 }
 
 template <typename T>
