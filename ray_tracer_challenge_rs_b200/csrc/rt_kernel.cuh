@@ -721,7 +721,10 @@ RT_DEV void trace_bvh(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<
 // object-space transform and the query bookkeeping exist ONCE in the instruction stream instead of once
 // per shape type.  The render kernel is bound by instruction-cache misses (GCC request rate), so code
 // bytes on the hot path matter more than the handful of extra instructions per shape.
-template <typename T, bool FULL, bool SMEM>
+// SHADOW_EXIT: a lane whose shadow query has found a blocker leaves the loop.  Pays when whole warps are in
+// the same query (wavefront family: -8 % on cover); in the persistent kernel, where the lanes of a warp are in
+// different queries, the extra branch costs more than the idle lanes save.
+template <typename T, bool FULL, bool SHADOW_EXIT, bool SMEM>
 RT_DEV void trace_unified(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
     const uint32_t n = sv.L.type_begin[NUM_SHAPE_TYPES];
     for (uint32_t pos = 0; pos < n; ++pos) {
@@ -751,6 +754,8 @@ RT_DEV void trace_unified(const SceneView<T, SMEM>& sv, const Ray<T>& ray, Trace
         default: if (FULL) k = local_intersect<T, 5>(local, g, meta.z, sv.triangle(pos), t0, t1, t2, t3); break;
         }
         consume<T, 4>(acc, k, t0, t1, t2, t3, (int)pos, meta);
+        // World::is_in_shadow (world.rs:106-111) is an `any`: a lane that has found a blocker is done
+        if (SHADOW_EXIT && acc.mode == MODE_SHADOW && acc.best_pos >= 0) break;
     }
 }
 
@@ -1020,7 +1025,7 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
         acc.c->all_t = acc.c->excl_t = T(0);
         acc.c->all_orig = acc.c->excl_orig = 0;
 #if RT_UNIFIED_LOOP
-        if (acc.mode != MODE_IDLE) trace_unified<T, FULL>(sv, ray, acc);  // uniform list (BVH scenes: the unbounded shapes)
+        if (acc.mode != MODE_IDLE) trace_unified<T, FULL, false>(sv, ray, acc);  // uniform list (BVH scenes: the unbounded shapes)
 #else
         if (acc.mode != MODE_IDLE) trace<T, FULL>(sv, ray, acc);  // uniform lists (BVH scenes: the unbounded shapes)
 #endif

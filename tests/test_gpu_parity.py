@@ -350,3 +350,17 @@ def test_auto_family_measures_then_settles(monkeypatch):
     flat, camera = load_scene_fixture("three_sphere_scene")
     with Renderer(flat) as r:
         assert [r.render(camera.resized(160, 80))[2]["family"] for _ in range(5)] == ["persistent"] * 5
+
+
+@pytest.mark.timeout(180, method="thread")
+def test_wavefront_bvh_large_frame_terminates_and_matches_persistent():
+    """Regression: with 10^4 shapes at >= 720p the level-0 launch of one build never finished (full-mask warp
+    votes in the BVH leaf batching; see trace_bvh).  Bit-equality with the persistent family on the same frame."""
+    from ray_tracer_challenge_rs_b200.synthetic import synthetic_camera, synthetic_scene
+
+    flat, cam = synthetic_scene(10000), synthetic_camera(1280, 720)
+    with Renderer(flat) as r:
+        a, _, sa = r.render(cam, want_rgb8=False, family="persistent")
+        b, _, sb = r.render(cam, want_rgb8=False, family="wavefront")
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    assert {k: sa[k] for k in COUNTERS} == {k: sb[k] for k in COUNTERS}
