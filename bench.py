@@ -86,6 +86,24 @@ class ClockSampler:
         self._thread = None
 
     def _run(self):
+        # NVML directly when the binding is there (a query takes ~1 ms, so even a 50 ms timed region gets several
+        # samples); otherwise the nvidia-smi query of the profiling recipe (a process spawn per sample)
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self.device_index)
+            bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop.is_set():
+                mask = int(get_reasons(handle))
+                self.samples.append([str(self.device_index), str(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)),
+                                     str(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)), "0"] +
+                                    ["Active" if mask & bit else "Not Active" for _, bit in bits])
+                self._stop.wait(0.005)
+            return
+        except Exception:
+            pass
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.device_index)],
@@ -199,6 +217,25 @@ def run_reference(args):
 
 RESULT_LINE = []  # filled by the arm that ran; printed by main() once stdout is back
 CALIBRATION_FRAMES = 4  # 2 per kernel family (TUNE_RUNS in csrc/rtgpu.cu)
+
+
+def profiled_traffic(args, family: str):
+    """DRAM bytes per frame (dram__bytes_read.sum + dram__bytes_write.sum over all launches of one frame) from the
+    committed ncu launch list, for the configuration it was captured on; None for anything else."""
+    if (args.scene, args.width, args.height, args.precision, args.max_depth, family) != ("cover", 1920, 1080, "f64", 6, "wavefront"):
+        return None, None
+    path = os.path.join(ROOT, "profiles", "r1_wavefront_launches.csv")
+    if not os.path.exists(path):
+        return None, None
+    import csv
+
+    total = 0.0
+    with open(path) as f:
+        for r in csv.reader(f):
+            if len(r) > 10 and r[-3] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[-2], 1.0)
+                total += float(r[-1].replace(",", "")) * scale
+    return (total or None), "profiles/r1_wavefront_launches.csv (ncu, all 22 launches of one frame)"
 
 
 def launches_per_frame(family: str, max_depth: int) -> int:
@@ -343,10 +380,13 @@ def run_b200(args):
         # ---- roofline of the render kernel: FP-pipe ----
         peak_tflops, _ = measure_fma_peak(args.precision, device=local_rank)
         flops = frame_flops(flat, stats)  # whole frame, all ranks
+        traffic, traffic_source = profiled_traffic(args, family_used)
         achieved = flops / world / (device_ms / K * 1e-3) / 1e12  # per device: each renders 1/N of the frame in device_ms/K
         roofline = {
             "bound": "fp64_fma_pipe" if args.precision == "f64" else "fp32_fma_pipe", "achieved": achieved, "peak": peak_tflops,
-            "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": None,
+            "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": traffic, "traffic_source": traffic_source,
+            "kernel": "rt::wf_level_kernel x (max_depth + 1) = 93 % of the step (profiles/r1_wavefront_launches.md); achieved = "
+                      "frame flops / frame time" if family_used == "wavefront" else "rt::render_kernel (the whole step)",
             "peak_source": "measured live: 8 independent FMA chains per thread on every SM (rtgpu_measure_fma_peak); "
                            "MEASURED_PEAKS.json holds only HBM and bf16 peaks",
             "algorithmic_flops_per_frame": flops, "flops_per_ray": flops_per_ray(flat),
