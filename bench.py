@@ -84,26 +84,36 @@ class ClockSampler:
         self.samples = []
         self._stop = threading.Event()
         self._thread = None
-
-    def _run(self):
-        # NVML directly when the binding is there (a query takes ~1 ms, so even a 50 ms timed region gets several
-        # samples); otherwise the nvidia-smi query of the profiling recipe (a process spawn per sample)
+        # NVML directly when the binding is there (a query takes ~2 ms, so even a 15 ms timed region gets several
+        # samples; initialised here, before the timed region); otherwise the nvidia-smi query of the profiling
+        # recipe (a process spawn per sample)
+        self._nvml = None
         try:
             import pynvml
 
             pynvml.nvmlInit()
-            handle = pynvml.nvmlDeviceGetHandleByIndex(self.device_index)
-            bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
-            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
-            while not self._stop.is_set():
-                mask = int(get_reasons(handle))
-                self.samples.append([str(self.device_index), str(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)),
-                                     str(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)), "0"] +
-                                    ["Active" if mask & bit else "Not Active" for _, bit in bits])
-                self._stop.wait(0.005)
-            return
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            reasons(handle)
+            self._nvml = (pynvml, handle, reasons)
         except Exception:
-            pass
+            self._nvml = None
+
+    def _run(self):
+        if self._nvml is not None:
+            pynvml, handle, reasons = self._nvml
+            bits = (0x8, 0x40, 0x20, 0x4)  # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+            while not self._stop.is_set():
+                try:
+                    mask = int(reasons(handle))
+                    self.samples.append([str(self.device_index), str(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)),
+                                         str(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)), "0"] +
+                                        ["Active" if mask & bit else "Not Active" for bit in bits])
+                except Exception:
+                    break
+                self._stop.wait(0.002)
+            if self.samples:
+                return
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.device_index)],
