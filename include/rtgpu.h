@@ -224,6 +224,9 @@ void rtgpu_context_destroy(rtgpu_context *context);
  * d_out_rgb[(k*hsize + x)*3 + c] for the k-th selected row.  d_counters is a DEVICE pointer to 6
  * uint64 (order of rtgpu_stats' first six fields) that the kernel adds into, or NULL.
  * In RTGPU_PRECISION_F32 d_out_rgb is `float*`-typed storage (still 3 values per pixel).
+ * Asynchrony: only the PERSISTENT family returns without waiting.  A WAVEFRONT frame is complete on return, and
+ * in automatic mode the calibration frames of a (scene, frame shape) wait for the previous frame's events; pass
+ * RTGPU_FLAG_PERSISTENT to keep a pipeline of frames fully asynchronous.
  */
 int rtgpu_context_render_device(rtgpu_context *context, const rtgpu_camera *camera,
                                 const rtgpu_opts *opts, const rtgpu_rows *rows, void *d_out_rgb,
