@@ -245,13 +245,13 @@ def profiled_traffic(args, family: str):
             if len(r) > 10 and r[-3] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[-2], 1.0)
                 total += float(r[-1].replace(",", "")) * scale
-    return (total or None), "profiles/r1_wavefront_launches.csv (ncu, all 22 launches of one frame)"
+    return (total or None), "profiles/r1_wavefront_launches.csv (ncu, every launch of one frame)"
 
 
 def launches_per_frame(family: str, max_depth: int) -> int:
     """Kernels of this library per frame: the persistent family is one launch; the wavefront family is a level
-    kernel + a queue-advance kernel per recursion level, a combine kernel per level and one counter commit."""
-    return 1 if family == "persistent" else 3 * (max_depth + 1) + 1
+    kernel and a combine kernel per recursion level and one counter commit."""
+    return 1 if family == "persistent" else 2 * (max_depth + 1) + 1
 
 
 def run_b200(args):

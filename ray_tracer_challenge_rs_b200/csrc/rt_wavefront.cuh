@@ -67,6 +67,7 @@ struct WfCounts {
     unsigned node_end[16 + 2]; // nodes created by levels 0..d end at node_end[d] (node_end[-1] = 0 implied)
     unsigned n_nodes;          // nodes allocated so far
     unsigned work;             // chunk cursor of the running launch
+    unsigned done;             // CTAs of the running launch that have finished (the last one closes the level)
     unsigned overflow;         // a queue or the node array was too small: the frame must be re-rendered
 };
 
@@ -135,7 +136,6 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
     sv.L = layout;
     sv.reals = g_reals;
     sv.ints = g_ints;
-    if constexpr (SMEM) stage_scene<T>(layout, g_reals, g_ints);
 
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t tiles_x = (cam.hsize + TILE_W - 1) / TILE_W;
@@ -155,6 +155,9 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
     const int n_lights = (int)layout.n_lights;
     const int remaining = (int)cam.max_depth - level;
     unsigned int c_primary = 0, c_shadow = 0, c_reflect = 0, c_refract = 0, c_nodes = 0;
+    if constexpr (SMEM) {
+        if (n_items) stage_scene<T>(layout, g_reals, g_ints);  // (uniform over the grid) nothing queued: nothing to stage
+    }
 
     for (;;) {
         // one warp = 32 consecutive work items (one 8x4 tile of pixels, or 32 neighbouring queue entries)
@@ -408,7 +411,7 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                     if (child_hit) {
                         const unsigned below = (1u << lane) - 1u;
                         const unsigned f = fbase + __popc(queued_front & below), bk = bbase + __popc(queued_back & below);
-                        // both ends grow towards each other; wf_advance_kernel compares their sum with the capacity
+                        // both ends grow towards each other; the last CTA of the launch compares their sum with the capacity
                         // once the launch is over (an overlap garbles entries of a frame that is re-rendered anyway)
                         const unsigned q = glass ? cap_rays - 1u - bk : f;
                         if ((glass ? bk : f) < cap_rays) {
@@ -482,13 +485,21 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
         for (int o = 16; o > 0; o >>= 1) px += __shfl_xor_sync(0xffffffffu, px, o);
         if (lane == 0 && px) atomicAdd(&counters[COUNTER_PIXELS], (unsigned long long)px);
     }
-}
 
-// Called between levels: remember where this level's nodes end, reset the chunk cursor.
-__global__ void wf_advance_kernel(WfCounts* counts, int level, unsigned cap_rays) {
-    counts->node_end[level] = counts->n_nodes;
-    counts->work = 0u;
-    if ((unsigned long long)counts->n_rays[level + 1] + counts->n_back[level + 1] > cap_rays) counts->overflow = 1u;
+    // The last CTA to finish closes the level (no separate launch): remember where this level's nodes end, reset
+    // the chunk cursor for the next launch, and check that the two ends of the next queue did not meet.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&counts->done, 1u) == gridDim.x - 1u) {
+            __threadfence();
+            volatile WfCounts* c = counts;
+            c->node_end[level] = c->n_nodes;
+            c->work = 0u;
+            c->done = 0u;
+            if ((unsigned long long)c->n_rays[level + 1] + c->n_back[level + 1] > cap_rays) c->overflow = 1u;
+        }
+    }
 }
 
 // World::shade_hit's tail (world.rs:59-66) for the nodes of one level, deepest level first.

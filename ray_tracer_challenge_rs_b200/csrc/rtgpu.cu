@@ -753,8 +753,6 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
         level_kernel<<<grid, RT_WF_THREADS, smem, stream>>>(d_reals, ctx->d_ints, lay, cam, level, in, out, (unsigned)ctx->wf_cap_rays, nodes,
                                                             (unsigned)ctx->wf_cap_nodes, ctx->d_wf_counts, d_out, d_out8, ctx->d_wf_priv);
         CUDA_TRY(cudaGetLastError());
-        rt::wf_advance_kernel<<<1, 1, 0, stream>>>(ctx->d_wf_counts, level, (unsigned)ctx->wf_cap_rays);
-        CUDA_TRY(cudaGetLastError());
         if (debug_sync) {
             const double t0 = wall_ms();
             CUDA_TRY(cudaStreamSynchronize(stream));
