@@ -400,11 +400,20 @@ RT_DEV void cube_check_axis_native(T origin, T direction, T& tmin, T& tmax) {
     tmax = dmax;
 }
 
+// Everything by value: a reference parameter of an out-of-line function pins the caller's object in local memory
+// (the object-space ray was stored there before every cube test although this fallback almost never runs).
 template <typename T>
-RT_COLD void cube_axes_native(const Ray<T>& r, T& xmin, T& xmax, T& ymin, T& ymax, T& zmin, T& zmax) {
-    cube_check_axis_native(r.o.x, r.d.x, xmin, xmax);
-    cube_check_axis_native(r.o.y, r.d.y, ymin, ymax);
-    cube_check_axis_native(r.o.z, r.d.z, zmin, zmax);
+struct CubeSlabs {
+    T xmin, xmax, ymin, ymax, zmin, zmax;
+};
+
+template <typename T>
+RT_COLD CubeSlabs<T> cube_axes_native(V3<T> o, V3<T> d) {
+    CubeSlabs<T> s;
+    cube_check_axis_native(o.x, d.x, s.xmin, s.xmax);
+    cube_check_axis_native(o.y, d.y, s.ymin, s.ymax);
+    cube_check_axis_native(o.z, d.z, s.zmin, s.zmax);
+    return s;
 }
 
 // shapes/cube.rs:22-43 without branches: both slab distances share one reciprocal; `ok` turns false
@@ -473,7 +482,12 @@ RT_DEV int local_intersect(const Ray<T>& r, const T* g, int flags, const T* tri,
         cube_axis_fast(r.o.x, r.d.x, xmin, xmax, ok);
         cube_axis_fast(r.o.y, r.d.y, ymin, ymax, ok);
         cube_axis_fast(r.o.z, r.d.z, zmin, zmax, ok);
-        if (!ok) cube_axes_native(r, xmin, xmax, ymin, ymax, zmin, zmax);
+        if (!ok) {
+            const CubeSlabs<T> s = cube_axes_native(r.o, r.d);
+            xmin = s.xmin; xmax = s.xmax;
+            ymin = s.ymin; ymax = s.ymax;
+            zmin = s.zmin; zmax = s.zmax;
+        }
         T dmin = fmax(fmax(fmax(-Real<T>::max(), xmin), ymin), zmin);
         T dmax = fmin(fmin(fmin(Real<T>::max(), xmax), ymax), zmax);
         if (dmin < dmax && dmax > T(0)) {
