@@ -1032,12 +1032,14 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
         acc.dir_sq = fma(ray.d.z, ray.d.z, fma(ray.d.y, ray.d.y, ray.d.x * ray.d.x));
         acc.best_orig = 0x7fffffff;
         acc.best_pos = -1;
-        acc.c->t_hit = t_hit;
-        acc.c->hit_class = (state == ST_CONTAINER) ? sv.shape_meta((uint32_t)hit_pos).w : -1;
-        acc.c->hit_class_inside = false;
-        acc.c->all_pos = acc.c->excl_pos = -1;
-        acc.c->all_t = acc.c->excl_t = T(0);
-        acc.c->all_orig = acc.c->excl_orig = 0;
+        if (state == ST_CONTAINER) {  // the container bookkeeping lives in local memory: only touch it when it is used
+            acc.c->t_hit = t_hit;
+            acc.c->hit_class = sv.shape_meta((uint32_t)hit_pos).w;
+            acc.c->hit_class_inside = false;
+            acc.c->all_pos = acc.c->excl_pos = -1;
+            acc.c->all_t = acc.c->excl_t = T(0);
+            acc.c->all_orig = acc.c->excl_orig = 0;
+        }
 #if RT_UNIFIED_LOOP
         if (acc.mode != MODE_IDLE) trace_unified<T, FULL, false>(sv, ray, acc);  // uniform list (BVH scenes: the unbounded shapes)
 #else

@@ -108,12 +108,14 @@ RT_DEV void wf_reset_acc(TraceAcc<T>& acc, int mode, const Ray<T>& ray, T best_t
     acc.dir_sq = fma(ray.d.z, ray.d.z, fma(ray.d.y, ray.d.y, ray.d.x * ray.d.x));
     acc.best_orig = 0x7fffffff;
     acc.best_pos = -1;
-    acc.c->t_hit = T(0);
-    acc.c->hit_class = -1;
-    acc.c->hit_class_inside = false;
-    acc.c->all_pos = acc.c->excl_pos = -1;
-    acc.c->all_t = acc.c->excl_t = T(0);
-    acc.c->all_orig = acc.c->excl_orig = 0;
+    if (mode == MODE_CONTAINER) {  // the container bookkeeping lives in local memory: only touch it when it is used
+        acc.c->t_hit = T(0);
+        acc.c->hit_class = -1;
+        acc.c->hit_class_inside = false;
+        acc.c->all_pos = acc.c->excl_pos = -1;
+        acc.c->all_t = acc.c->excl_t = T(0);
+        acc.c->all_orig = acc.c->excl_orig = 0;
+    }
 }
 
 template <typename T, bool FULL, bool BVH, bool SMEM>
