@@ -209,6 +209,7 @@ struct SceneView {
     RT_DEV const int* pattern_meta(uint32_t p) const { return I() + L.pat_meta_off + p * PAT_INTS; }
     RT_DEV const T* light(uint32_t l) const { return R() + L.light_off + (size_t)l * LIGHT_REALS; }
     RT_DEV const T* cull(uint32_t pos) const { return R() + L.cull_off + (size_t)pos * CULL_REALS; }
+    RT_DEV T cull_shrink() const { return sizeof(T) == 8 ? (T)L.cull_shrink64 : (T)L.cull_shrink32; }
 };
 
 // Copy both scene blobs to the start of dynamic shared memory with the TMA unit: two bulk asynchronous copies
@@ -582,6 +583,17 @@ RT_DEV int local_intersect(const Ray<T>& r, const T* g, int flags, const T* tri,
     return n;
 }
 
+// A cull record (centre[3], radius^2) is 16-byte aligned in both precisions: two 128-bit loads (one in f32)
+// instead of four scalar ones.
+RT_DEV void load_cull(const double* p, double& x, double& y, double& z, double& w) {
+    const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
+    x = a.x; y = a.y; z = b.x; w = b.y;
+}
+RT_DEV void load_cull(const float* p, float& x, float& y, float& z, float& w) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0];
+    x = a.x; y = a.y; z = a.z; w = a.w;
+}
+
 // Ray::intersect (ray.rs:35-49) for the shape at sorted position `pos`, of (compile-time) type TYPE:
 // object-space ray, local_intersect, then the query's bookkeeping.
 template <typename T, int TYPE, bool SMEM>
@@ -615,7 +627,7 @@ RT_DEV void trace_type(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc
             const T ocx = cs[0] - ray.o.x, ocy = cs[1] - ray.o.y, ocz = cs[2] - ray.o.z;
             const T bq = fma(ocz, ray.d.z, fma(ocy, ray.d.y, ocx * ray.d.x));
             const T c2 = fma(ocz, ocz, fma(ocy, ocy, ocx * ocx));
-            const T ex = fma(c2, Real<T>::cull_shrink(), -cs[3]);
+            const T ex = fma(c2, sv.cull_shrink(), -cs[3]);
             if (ex > T(0) && ((acc.mode != MODE_CONTAINER && bq < T(0)) || ex * acc.dir_sq > bq * bq)) continue;
         }
 #endif
@@ -744,11 +756,12 @@ RT_DEV void trace_unified(const SceneView<T, SMEM>& sv, const Ray<T>& ray, Trace
     for (uint32_t pos = 0; pos < n; ++pos) {
 #if RT_CULL
         {
-            const T* cs = sv.cull(pos);  // see trace_type; unbounded shapes carry r2 = +inf and always pass
-            const T ocx = cs[0] - ray.o.x, ocy = cs[1] - ray.o.y, ocz = cs[2] - ray.o.z;
+            T cx, cy, cz, r2;  // see trace_type; unbounded shapes carry r2 = +inf and always pass
+            load_cull(sv.cull(pos), cx, cy, cz, r2);
+            const T ocx = cx - ray.o.x, ocy = cy - ray.o.y, ocz = cz - ray.o.z;
             const T bq = fma(ocz, ray.d.z, fma(ocy, ray.d.y, ocx * ray.d.x));
             const T c2 = fma(ocz, ocz, fma(ocy, ocy, ocx * ocx));
-            const T ex = fma(c2, Real<T>::cull_shrink(), -cs[3]);
+            const T ex = fma(c2, sv.cull_shrink(), -r2);
             if (ex > T(0) && ((acc.mode != MODE_CONTAINER && bq < T(0)) || ex * acc.dir_sq > bq * bq)) continue;
         }
 #endif

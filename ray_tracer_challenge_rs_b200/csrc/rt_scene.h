@@ -92,6 +92,10 @@ struct SceneLayout {
     int32_t bvh_root;                               // root reference (>= 0 node, < 0 single leaf)
     uint32_t n_reals, n_ints;                       // blob sizes
     uint32_t in_shared;                             // 1: CTAs stage both blobs in shared memory
+    // shrink factor of the bounding-sphere pre-test (>> the rounding of the pre-test itself).  Lives here so that
+    // the loop reads it as a constant-bank operand instead of rebuilding the literal every iteration.
+    float cull_shrink32;
+    double cull_shrink64;
 };
 
 // Camera (composites/camera.rs:10-19) + the row selection of one launch (include/rtgpu.h rtgpu_rows).

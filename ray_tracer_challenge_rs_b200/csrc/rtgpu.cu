@@ -287,6 +287,8 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     rt::SceneLayout& lay = out->layout;
     memset(&lay, 0, sizeof(lay));
     lay.n_shapes = S;
+    lay.cull_shrink64 = 1.0 - 1.0e-9;
+    lay.cull_shrink32 = 1.0f - 1.0e-3f;
     lay.n_materials = M;
     lay.n_patterns = Q;
     lay.n_lights = L;
@@ -351,7 +353,7 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     lay.mat_off = lay.tri_off + n_tri * rt::TRI_REALS;
     lay.pat_off = lay.mat_off + M * rt::MAT_REALS;
     lay.light_off = lay.pat_off + Q * rt::PAT_REALS;
-    lay.cull_off = (lay.light_off + L * rt::LIGHT_REALS + 1u) & ~1u;  // 16-byte aligned records
+    lay.cull_off = (lay.light_off + L * rt::LIGHT_REALS + 3u) & ~3u;  // 16-byte aligned records in f32 too
     lay.bvh_off = lay.cull_off + S * rt::CULL_REALS;
     lay.n_reals = lay.bvh_off + lay.n_bvh_nodes * rt::BVH_REALS;
     lay.n_reals = (lay.n_reals + 3u) & ~3u;  // 16-byte multiple in f32 too (bulk copies into shared memory)
