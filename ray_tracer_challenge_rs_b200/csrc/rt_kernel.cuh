@@ -609,32 +609,6 @@ RT_DEV void test_shape(const SceneView<T, SMEM>& sv, uint32_t pos, const Ray<T>&
     consume<T, NMAX>(acc, n, t0, t1, t2, t3, (int)pos, meta);
 }
 
-// World::collect_intersections (world.rs:25-35) over the flat per-type lists: every shape, no dispatch.
-template <typename T, int TYPE, bool SMEM>
-RT_DEV void trace_type(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
-    const uint32_t b = sv.L.type_begin[TYPE], e = sv.L.type_begin[TYPE + 1];
-    for (uint32_t pos = b; pos < e; ++pos) {
-#if RT_CULL
-        if (TYPE != 1) {  // planes are unbounded
-            // Conservative pre-test against the shape's world-space bounding sphere (centre c, radius^2
-            // r2, inflated by the packer).  With oc = c - o and bq = oc.d, the ray's supporting line
-            // misses the sphere iff |oc|^2 |d|^2 - bq^2 > r2 |d|^2; if the origin is outside and the
-            // centre behind it (bq < 0) every intersection has a negative distance, which only the
-            // container walk cares about.  The shrink factor dwarfs the rounding of this test, and the
-            // inflation dwarfs the rounding of the exact test, so a culled shape yields no
-            // intersection in the reference's arithmetic either.
-            const T* cs = sv.cull(pos);
-            const T ocx = cs[0] - ray.o.x, ocy = cs[1] - ray.o.y, ocz = cs[2] - ray.o.z;
-            const T bq = fma(ocz, ray.d.z, fma(ocy, ray.d.y, ocx * ray.d.x));
-            const T c2 = fma(ocz, ocz, fma(ocy, ocy, ocx * ocx));
-            const T ex = fma(c2, sv.cull_shrink(), -cs[3]);
-            if (ex > T(0) && ((acc.mode != MODE_CONTAINER && bq < T(0)) || ex * acc.dir_sq > bq * bq)) continue;
-        }
-#endif
-        test_shape<T, TYPE>(sv, pos, ray, acc);
-    }
-}
-
 // ---- BVH traversal (scenes with many bounded shapes; rt_bvh.h) -----------------------------------
 // Each lane walks the hierarchy with its own small stack.  A child is entered iff the ray's parameter
 // interval inside its (inflated) box meets the interval the query still cares about:
@@ -743,10 +717,18 @@ RT_DEV void trace_bvh(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<
     }
 }
 
-// One loop over the uniform shape list with a warp-uniform switch on the shape type: the pre-test, the
-// object-space transform and the query bookkeeping exist ONCE in the instruction stream instead of once
-// per shape type.  The render kernel is bound by instruction-cache misses (GCC request rate), so code
-// bytes on the hot path matter more than the handful of extra instructions per shape.
+// World::collect_intersections (world.rs:25-35) over the uniform list.  One loop with a warp-uniform switch on
+// the shape type: the pre-test, the object-space transform and the query bookkeeping exist ONCE in the instruction
+// stream instead of once per shape type.  The kernels are bound by instruction supply (GPC instruction cache
+// request rate), so code bytes on the hot path matter more than the handful of extra instructions per shape; the
+// earlier one-loop-per-type version was 7 % slower.
+//
+// Conservative pre-test against the shape's world-space bounding sphere (centre c, radius^2 r2, inflated by the
+// packer).  With oc = c - o and bq = oc.d, the ray's supporting line misses the sphere iff
+// |oc|^2 |d|^2 - bq^2 > r2 |d|^2; if the origin is outside and the centre behind it (bq < 0) every intersection has
+// a negative distance, which only the container walk cares about.  The shrink factor dwarfs the rounding of this
+// test, and the inflation dwarfs the rounding of the exact test, so a culled shape yields no intersection in the
+// reference's arithmetic either.  Shapes without a finite sphere carry r2 = +inf and always pass.
 // SHADOW_EXIT: a lane whose shadow query has found a blocker leaves the loop.  Pays when whole warps are in
 // the same query (wavefront family: -8 % on cover); in the persistent kernel, where the lanes of a warp are in
 // different queries, the extra branch costs more than the idle lanes save.
@@ -756,7 +738,7 @@ RT_DEV void trace_unified(const SceneView<T, SMEM>& sv, const Ray<T>& ray, Trace
     for (uint32_t pos = 0; pos < n; ++pos) {
 #if RT_CULL
         {
-            T cx, cy, cz, r2;  // see trace_type; unbounded shapes carry r2 = +inf and always pass
+            T cx, cy, cz, r2;
             load_cull(sv.cull(pos), cx, cy, cz, r2);
             const T ocx = cx - ray.o.x, ocy = cy - ray.o.y, ocz = cz - ray.o.z;
             const T bq = fma(ocz, ray.d.z, fma(ocy, ray.d.y, ocx * ray.d.x));
@@ -785,21 +767,6 @@ RT_DEV void trace_unified(const SceneView<T, SMEM>& sv, const Ray<T>& ray, Trace
         if (SHADOW_EXIT && acc.mode == MODE_SHADOW && acc.best_pos >= 0) break;
     }
 }
-
-// FULL = false: the scene holds only spheres, planes and cubes (all but one shipped scene); the
-// cylinder / cone / triangle loops are not even instantiated, which keeps the code footprint down.
-template <typename T, bool FULL, bool SMEM>
-RT_DEV void trace(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
-    trace_type<T, 0>(sv, ray, acc);
-    trace_type<T, 1>(sv, ray, acc);
-    trace_type<T, 2>(sv, ray, acc);
-    if (FULL) {
-        trace_type<T, 3>(sv, ray, acc);
-        trace_type<T, 4>(sv, ray, acc);
-        trace_type<T, 5>(sv, ray, acc);
-    }
-}
-
 
 // utils.rs:16-24
 template <typename T> RT_DEV bool coarse_eq(T a, T b) { return a == b || fabs(a - b) < Real<T>::eps(); }
@@ -894,9 +861,6 @@ enum : int { ST_FETCH = 0, ST_RADIANCE = 1, ST_CONTAINER = 2, ST_SHADOW = 3, ST_
 #define RT_TMA_STAGE 1  // scene tables -> shared memory by cp.async.bulk + mbarrier (0: plain loads)
 #endif
 
-#ifndef RT_UNIFIED_LOOP
-#define RT_UNIFIED_LOOP 1
-#endif
 
 #ifndef RT_PHASE_SYNC
 #define RT_PHASE_SYNC 0
@@ -1053,11 +1017,7 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
             acc.c->all_t = acc.c->excl_t = T(0);
             acc.c->all_orig = acc.c->excl_orig = 0;
         }
-#if RT_UNIFIED_LOOP
         if (acc.mode != MODE_IDLE) trace_unified<T, FULL, false>(sv, ray, acc);  // uniform list (BVH scenes: the unbounded shapes)
-#else
-        if (acc.mode != MODE_IDLE) trace<T, FULL>(sv, ray, acc);  // uniform lists (BVH scenes: the unbounded shapes)
-#endif
         if (BVH) trace_bvh<T, FULL>(sv, ray, acc);  // every lane takes part: warp votes inside
 
 #if RT_PHASE_SYNC

@@ -69,7 +69,7 @@ constexpr int LIGHT_REALS = 6;
 // ---- cull record: 4 reals: world-space bounding sphere centre[3], radius^2 (+inf = unbounded) ----
 // Not part of the reference: a conservative pre-test.  A ray whose supporting line stays outside the
 // (slightly inflated) sphere cannot produce an intersection in the reference's arithmetic either, so
-// skipping the exact test changes no result (rt_kernel.cuh, trace_type).
+// skipping the exact test changes no result (rt_kernel.cuh, trace_unified).
 constexpr int CULL_REALS = 4;
 
 // ---- BVH node (not in the reference; csrc/rt_bvh.h builds it): 12 reals = the two children's

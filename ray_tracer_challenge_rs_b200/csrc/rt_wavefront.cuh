@@ -120,11 +120,7 @@ RT_DEV void wf_reset_acc(TraceAcc<T>& acc, int mode, const Ray<T>& ray, T best_t
 
 template <typename T, bool FULL, bool BVH, bool SMEM>
 RT_DEV void wf_trace(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
-#if RT_UNIFIED_LOOP
     if (acc.mode != MODE_IDLE) trace_unified<T, FULL, true>(sv, ray, acc);
-#else
-    if (acc.mode != MODE_IDLE) trace<T, FULL>(sv, ray, acc);
-#endif
     if (BVH) trace_bvh<T, FULL>(sv, ray, acc);  // warp votes inside: every lane takes part
 }
 
