@@ -541,6 +541,7 @@ struct rtgpu_context {
     cudaEvent_t tune_ev0 = nullptr, tune_ev1 = nullptr;
     int tune_pending_family = -1;  // a trial whose events have been recorded but not read yet
     uint64_t tune_pending_key = 0;
+    uint64_t tune_last_key = 0;    // key of the host-buffer render in flight
     int last_family = 0;
 };
 
@@ -673,6 +674,17 @@ int resolve_family(rtgpu_context* ctx, const rtgpu_opts* opts, uint64_t key, boo
     return entry->best_ms[FAMILY_WAVEFRONT] < entry->best_ms[FAMILY_PERSISTENT] ? FAMILY_WAVEFRONT : FAMILY_PERSISTENT;
 }
 
+// The wavefront family cannot get its buffers for this frame shape: automatic mode stays with the persistent kernel.
+void tune_rule_out_wavefront(rtgpu_context* ctx, uint64_t key) {
+    cudaGetLastError();
+    for (auto& e : ctx->tune)
+        if (e.key == key) {
+            e.runs[FAMILY_PERSISTENT] = e.runs[FAMILY_WAVEFRONT] = TUNE_RUNS;
+            e.best_ms[FAMILY_PERSISTENT] = 0.0f;
+            e.best_ms[FAMILY_WAVEFRONT] = 1e30f;
+        }
+}
+
 void tune_begin(rtgpu_context* ctx, cudaStream_t stream) { cudaEventRecord(ctx->tune_ev0, stream); }
 
 void tune_end(rtgpu_context* ctx, cudaStream_t stream, uint64_t key, int family) {
@@ -692,6 +704,13 @@ int wavefront_reserve(rtgpu_context* ctx, uint64_t pixels, double growth) {
     want_rays = std::min<size_t>(want_rays, 0xFFFFFF00u);
     want_nodes = std::min<size_t>(want_nodes, 0x7FFFFF00u);
     const size_t bytes_rays = want_rays * sizeof(rt::WfRay<T>), bytes_nodes = want_nodes * sizeof(rt::WfNode<T>);
+    // RTGPU_WF_MAX_BYTES caps what the family may hold on a device (two queues + the node array)
+    if (const char* cap = getenv("RTGPU_WF_MAX_BYTES"); cap && *cap) {
+        const unsigned long long limit = strtoull(cap, nullptr, 10);
+        if (2ull * std::max(bytes_rays, ctx->wf_bytes_rays) + std::max(bytes_nodes, ctx->wf_bytes_nodes) > limit)
+            return fail(RTGPU_ERR_OUT_OF_MEMORY, "wavefront buffers (%zu B rays x 2 + %zu B nodes) exceed RTGPU_WF_MAX_BYTES=%llu", bytes_rays,
+                        bytes_nodes, limit);
+    }
     if (bytes_rays > ctx->wf_bytes_rays) {
         for (int k = 0; k < 2; ++k) {
             if (ctx->d_wf_rays[k]) cudaFree(ctx->d_wf_rays[k]);
@@ -1060,20 +1079,27 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
     const bool mappable = !(zc && zc[0] == '0') && (!out_rgb || map_rgb) && (!out_rgb8 || map_rgb8);
     bool trial = false;
     const uint64_t key = tune_key(ctx, camera, sel, precision, max_depth, 1u + (mappable ? 1u : 0u) + (out_rgb ? 2u : 0u) + (out_rgb8 ? 4u : 0u));
-    const int family = forced_family >= 0 ? forced_family : resolve_family(ctx, opts, key, &trial);
-    ctx->zero_copy = mappable && family == FAMILY_PERSISTENT;
-    if (!ctx->zero_copy) {
-        st = ensure_out_buffers(ctx, out_rgb ? row_rgb * n_rows : 0, out_rgb8 ? row_rgb8 * n_rows : 0);
-        if (st != RTGPU_OK) return st;
-    }
+    int family = forced_family >= 0 ? forced_family : resolve_family(ctx, opts, key, &trial);
+    ctx->tune_last_key = key;
     if (family == FAMILY_WAVEFRONT && n_rows && camera->hsize) {
         // allocate the queues before the timed region (cudaMalloc waits for the device)
         const uint64_t pixels = (uint64_t)camera->hsize * n_rows;
         const size_t ray_bytes = precision == RTGPU_PRECISION_F64 ? sizeof(rt::WfRay<double>) : sizeof(rt::WfRay<float>);
         if (ctx->wf_bytes_rays / ray_bytes < 3 * pixels / 2) {
             st = precision == RTGPU_PRECISION_F64 ? wavefront_reserve<double>(ctx, pixels, 1.0) : wavefront_reserve<float>(ctx, pixels, 1.0);
-            if (st != RTGPU_OK) return st;
+            if (st == RTGPU_ERR_OUT_OF_MEMORY && forced_family < 0 && requested_family(opts) == FAMILY_AUTO) {
+                tune_rule_out_wavefront(ctx, key);
+                family = FAMILY_PERSISTENT;
+                trial = false;
+            } else if (st != RTGPU_OK) {
+                return st;
+            }
         }
+    }
+    ctx->zero_copy = mappable && family == FAMILY_PERSISTENT;
+    if (!ctx->zero_copy) {
+        st = ensure_out_buffers(ctx, out_rgb ? row_rgb * n_rows : 0, out_rgb8 ? row_rgb8 * n_rows : 0);
+        if (st != RTGPU_OK) return st;
     }
     CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, rt::NUM_COUNTERS * sizeof(unsigned long long), ctx->stream));
     if (trial) tune_begin(ctx, ctx->stream);
@@ -1117,6 +1143,14 @@ int finish_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rtg
         const uint64_t pixels = (uint64_t)camera->hsize * count_rows(sel, camera->vsize);
         const bool f64 = !opts || opts->precision == RTGPU_PRECISION_F64;
         st = f64 ? wavefront_check<double>(ctx, pixels, ctx->stream) : wavefront_check<float>(ctx, pixels, ctx->stream);
+        if (st == RTGPU_ERR_OUT_OF_MEMORY && requested_family(opts) == FAMILY_AUTO) {
+            // the frame needs larger queues than the device can give: the persistent kernel needs none
+            tune_rule_out_wavefront(ctx, ctx->tune_last_key);
+            st = enqueue_host_render(ctx, camera, opts, rows, out_rgb, out_rgb8, FAMILY_PERSISTENT);
+            if (st != RTGPU_OK) return st;
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            break;
+        }
         if (st < 0) return st;
         if (st == 0) break;
         st = enqueue_host_render(ctx, camera, opts, rows, out_rgb, out_rgb8, FAMILY_WAVEFRONT);
@@ -1295,6 +1329,10 @@ int rtgpu_context_render_device(rtgpu_context* context, const rtgpu_camera* came
     const int family = resolve_family(context, opts, key, &trial);
     if (trial) tune_begin(context, stream);
     st = render_device_impl(context, camera, opts, rows, d_out_rgb, d_out_rgb8, d_counters, stream, nullptr, family);
+    if (st == RTGPU_ERR_OUT_OF_MEMORY && family == FAMILY_WAVEFRONT && requested_family(opts) == FAMILY_AUTO) {
+        tune_rule_out_wavefront(context, key);  // no room for the queues: the persistent kernel needs none
+        return render_device_impl(context, camera, opts, rows, d_out_rgb, d_out_rgb8, d_counters, stream, nullptr, FAMILY_PERSISTENT);
+    }
     if (trial && st == RTGPU_OK) tune_end(context, stream, key, family);
     return st;
 }

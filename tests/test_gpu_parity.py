@@ -16,6 +16,7 @@ import numpy as np
 import pytest
 
 from oracle.oracle import Oracle
+from ray_tracer_challenge_rs_b200 import abi
 from ray_tracer_challenge_rs_b200.fixtures import SHIPPED_SCENES, load_scene_fixture
 from ray_tracer_challenge_rs_b200.render import Renderer, device_count, render_gpu
 
@@ -364,3 +365,33 @@ def test_wavefront_bvh_large_frame_terminates_and_matches_persistent():
         b, _, sb = r.render(cam, want_rgb8=False, family="wavefront")
     assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
     assert {k: sa[k] for k in COUNTERS} == {k: sb[k] for k in COUNTERS}
+
+
+def test_auto_family_survives_without_room_for_the_queues(monkeypatch):
+    """RTGPU_WF_MAX_BYTES caps the wavefront family's buffers: automatic mode then stays with the persistent kernel
+    (also when only the enlarged buffers of an overflowing frame do not fit); asking for the family explicitly fails."""
+    monkeypatch.delenv("RTGPU_FAMILY", raising=False)
+    monkeypatch.delenv("RTGPU_WAVEFRONT", raising=False)
+    flat, camera = load_scene_fixture("refraction")
+    cam = camera.resized(256, 256)
+    with Renderer(flat) as r:
+        want, want8, _ = r.render(cam, family="persistent")
+    monkeypatch.setenv("RTGPU_WF_MAX_BYTES", "1000000")
+    with Renderer(flat) as r:
+        frames = [r.render(cam) for _ in range(4)]
+        assert [st["family"] for _, _, st in frames] == ["persistent"] * 4
+        assert all(np.array_equal(rgb.view(np.uint64), want.view(np.uint64)) and np.array_equal(rgb8, want8) for rgb, rgb8, _ in frames)
+        with pytest.raises(abi.RtgpuError) as err:
+            r.render(cam, family="wavefront")
+        assert err.value.status == abi.ERR_OUT_OF_MEMORY
+    # room for the first guess (3 rays + 5 nodes per pixel = 283 MB at 512x512) but not for what this frame needs
+    # (23 rays per pixel: test_wavefront_equals_persistent_bit_for_bit relies on the same overflow)
+    monkeypatch.delenv("RTGPU_WF_MAX_BYTES")
+    cam = camera.resized(512, 512)
+    with Renderer(flat) as r:
+        want, _, _ = r.render(cam, family="persistent", want_rgb8=False)
+    monkeypatch.setenv("RTGPU_WF_MAX_BYTES", str(300 * 1000 * 1000))
+    with Renderer(flat) as r:
+        frames = [r.render(cam, want_rgb8=False) for _ in range(4)]
+    assert all(np.array_equal(rgb.view(np.uint64), want.view(np.uint64)) for rgb, _, _ in frames)
+    assert [st["family"] for _, _, st in frames[1:]] == ["persistent"] * 3
