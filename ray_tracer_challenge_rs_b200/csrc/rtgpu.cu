@@ -11,6 +11,7 @@
 #include <cmath>
 #include <limits>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -529,6 +530,10 @@ struct rtgpu_context {
     size_t wf_cap_rays = 0, wf_cap_nodes = 0;  // in elements
     size_t wf_bytes_rays = 0, wf_bytes_nodes = 0;
     bool wf_used = false;  // the last launch took the wavefront path (overflow must be checked after it)
+    bool wf_keep_overflow = false;  // this launch continues a frame rendered in chunks: the overflow flag is sticky
+    // host-buffer renders in chunks (wavefront family): the copy of one chunk overlaps the kernels of the next
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_chunk = nullptr, ev_copied = nullptr;
     // kernel-family tuner (FAMILY_AUTO): per (scene, frame shape, path) the best time of each family
     bool has_secondary = false;
     uint64_t scene_fingerprint = 0;
@@ -698,9 +703,11 @@ void tune_end(rtgpu_context* ctx, cudaStream_t stream, uint64_t key, int family)
 
 template <typename T>
 int wavefront_reserve(rtgpu_context* ctx, uint64_t pixels, double growth) {
-    // first guess: 3 queued rays and 5 nodes per pixel; after an overflow the caller asks for more
-    size_t want_rays = std::max<size_t>((size_t)(3.0 * growth * (double)pixels), 1u << 16);
-    size_t want_nodes = std::max<size_t>((size_t)(5.0 * growth * (double)pixels), 1u << 16);
+    // first guess: 3 queued rays and 5 nodes per pixel; after an overflow the caller asks for more.
+    // RTGPU_WF_INITIAL_SCALE scales the guess (tests use a small one to exercise the enlarge-and-render-again path).
+    if (const char* e = getenv("RTGPU_WF_INITIAL_SCALE"); growth == 1.0 && e && *e && atof(e) > 0.0) growth = atof(e);
+    size_t want_rays = std::max<size_t>((size_t)(3.0 * growth * (double)pixels), 1u << 12);
+    size_t want_nodes = std::max<size_t>((size_t)(5.0 * growth * (double)pixels), 1u << 12);
     want_rays = std::min<size_t>(want_rays, 0xFFFFFF00u);
     want_nodes = std::min<size_t>(want_nodes, 0x7FFFFF00u);
     const size_t bytes_rays = want_rays * sizeof(rt::WfRay<T>), bytes_nodes = want_nodes * sizeof(rt::WfNode<T>);
@@ -764,7 +771,7 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
     if (!ctx->d_wf_counts || !ctx->d_wf_priv || !ctx->d_wf_nodes || !ctx->d_wf_rays[0] || !ctx->d_wf_rays[1])
         return fail(RTGPU_ERR_CUDA, "wavefront buffers missing (counts %p priv %p nodes %p rays %p %p, cap %zu %zu)", (void*)ctx->d_wf_counts,
                     (void*)ctx->d_wf_priv, ctx->d_wf_nodes, ctx->d_wf_rays[0], ctx->d_wf_rays[1], ctx->wf_cap_rays, ctx->wf_cap_nodes);
-    CUDA_TRY(cudaMemsetAsync(ctx->d_wf_counts, 0, sizeof(rt::WfCounts), stream));
+    CUDA_TRY(cudaMemsetAsync(ctx->d_wf_counts, 0, ctx->wf_keep_overflow ? offsetof(rt::WfCounts, overflow) : sizeof(rt::WfCounts), stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_wf_priv, 0, rt::NUM_COUNTERS * sizeof(unsigned long long), stream));
     (void)d_counters;
     rt::WfNode<T>* nodes = reinterpret_cast<rt::WfNode<T>*>(ctx->d_wf_nodes);
@@ -1017,6 +1024,9 @@ void context_release(rtgpu_context* ctx) {
     if (ctx->d_wf_priv) cudaFree(ctx->d_wf_priv);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_chunk) cudaEventDestroy(ctx->ev_chunk);
+    if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->tune_ev0) cudaEventDestroy(ctx->tune_ev0);
     if (ctx->tune_ev1) cudaEventDestroy(ctx->tune_ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1112,6 +1122,69 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
         if (trial) tune_end(ctx, ctx->stream, key, family);
         return RTGPU_OK;
     }
+    // Wavefront family, whole frame: render it as two interleaved halves (16-row bands, like two devices would) and
+    // copy the first half while the second one renders — the queues are reused, and the 1 ms copy of a 1080p f64
+    // frame is half hidden.  RTGPU_E2E_CHUNKS=1 disables.
+    const char* chunks_env = getenv("RTGPU_E2E_CHUNKS");
+    const bool chunked = family == FAMILY_WAVEFRONT && sel.shard_count == 1 && sel.band_rows >= camera->vsize && camera->vsize >= 64 &&
+                         (uint64_t)camera->hsize * camera->vsize >= (1u << 18) && !(chunks_env && chunks_env[0] == '1');
+    if (chunked) {
+        if (!ctx->copy_stream) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_chunk, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
+        }
+        constexpr uint32_t BAND = 16, CHUNKS = 2;
+        size_t rows_before = 0;
+        for (uint32_t c = 0; c < CHUNKS; ++c) {
+            rtgpu_rows sub;
+            sub.band_rows = BAND;
+            sub.shard_index = c;
+            sub.shard_count = CHUNKS;
+            RowSel sub_sel{BAND, c, CHUNKS};
+            const uint32_t rows_c = count_rows(sub_sel, camera->vsize);
+            char* d_rgb_c = out_rgb ? (char*)ctx->d_out + rows_before * row_rgb : nullptr;
+            uint8_t* d_rgb8_c = out_rgb8 ? ctx->d_out8 + rows_before * row_rgb8 : nullptr;
+            ctx->wf_keep_overflow = c > 0;
+            st = render_device_impl(ctx, camera, opts, &sub, d_rgb_c, d_rgb8_c, reinterpret_cast<uint64_t*>(ctx->d_counters), ctx->stream, nullptr,
+                                    family, false, /*wavefront_blocking=*/false);
+            ctx->wf_keep_overflow = false;
+            if (st != RTGPU_OK) return st;
+            // the last chunk's copies follow its kernels on the main stream; earlier ones go to the copy stream
+            cudaStream_t cs = ctx->stream;
+            if (c + 1 < CHUNKS) {
+                CUDA_TRY(cudaEventRecord(ctx->ev_chunk, ctx->stream));
+                CUDA_TRY(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk, 0));
+                cs = ctx->copy_stream;
+            } else {
+                CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+            }
+            // compact band b of this chunk -> image rows of band (b * CHUNKS + c): one strided copy + the partial last band
+            const uint32_t full_bands = rows_c / BAND, tail_rows = rows_c % BAND;
+            const size_t first_row = (size_t)c * BAND;
+            if (out_rgb) {
+                if (full_bands)
+                    CUDA_TRY(cudaMemcpy2DAsync((char*)out_rgb + first_row * row_rgb, (size_t)CHUNKS * BAND * row_rgb, d_rgb_c, (size_t)BAND * row_rgb,
+                                               (size_t)BAND * row_rgb, full_bands, cudaMemcpyDeviceToHost, cs));
+                if (tail_rows)
+                    CUDA_TRY(cudaMemcpyAsync((char*)out_rgb + (first_row + (size_t)full_bands * CHUNKS * BAND) * row_rgb,
+                                             d_rgb_c + (size_t)full_bands * BAND * row_rgb, (size_t)tail_rows * row_rgb, cudaMemcpyDeviceToHost, cs));
+            }
+            if (out_rgb8) {
+                if (full_bands)
+                    CUDA_TRY(cudaMemcpy2DAsync(out_rgb8 + first_row * row_rgb8, (size_t)CHUNKS * BAND * row_rgb8, d_rgb8_c, (size_t)BAND * row_rgb8,
+                                               (size_t)BAND * row_rgb8, full_bands, cudaMemcpyDeviceToHost, cs));
+                if (tail_rows)
+                    CUDA_TRY(cudaMemcpyAsync(out_rgb8 + (first_row + (size_t)full_bands * CHUNKS * BAND) * row_rgb8,
+                                             d_rgb8_c + (size_t)full_bands * BAND * row_rgb8, (size_t)tail_rows * row_rgb8, cudaMemcpyDeviceToHost, cs));
+            }
+            if (c + 1 < CHUNKS) CUDA_TRY(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+            rows_before += rows_c;
+        }
+        CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));  // the main stream ends after every copy
+        if (trial) tune_end(ctx, ctx->stream, key, family);
+        return RTGPU_OK;
+    }
     st = render_device_impl(ctx, camera, opts, rows, out_rgb ? ctx->d_out : nullptr, out_rgb8 ? ctx->d_out8 : nullptr,
                             reinterpret_cast<uint64_t*>(ctx->d_counters), ctx->stream, nullptr, family, false, /*wavefront_blocking=*/false);
     if (st != RTGPU_OK) return st;
@@ -1136,7 +1209,7 @@ int finish_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rtg
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     // wavefront family: if a queue or the node array was too small the buffers have been enlarged: render again
-    for (int attempt = 0; ctx->wf_used && attempt < 8; ++attempt) {
+    for (int attempt = 0; ctx->wf_used; ++attempt) {
         RowSel sel;
         int st = normalise_rows(rows, camera->vsize, &sel);
         if (st != RTGPU_OK) return st;
@@ -1153,6 +1226,7 @@ int finish_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rtg
         }
         if (st < 0) return st;
         if (st == 0) break;
+        if (attempt >= 8) return fail(RTGPU_ERR_OUT_OF_MEMORY, "wavefront buffers kept overflowing");
         st = enqueue_host_render(ctx, camera, opts, rows, out_rgb, out_rgb8, FAMILY_WAVEFRONT);
         if (st != RTGPU_OK) return st;
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));

@@ -387,6 +387,7 @@ def test_auto_family_survives_without_room_for_the_queues(monkeypatch):
     # room for the first guess (3 rays + 5 nodes per pixel = 283 MB at 512x512) but not for what this frame needs
     # (23 rays per pixel: test_wavefront_equals_persistent_bit_for_bit relies on the same overflow)
     monkeypatch.delenv("RTGPU_WF_MAX_BYTES")
+    monkeypatch.setenv("RTGPU_E2E_CHUNKS", "1")  # one launch sequence for the whole frame, as the sizes below assume
     cam = camera.resized(512, 512)
     with Renderer(flat) as r:
         want, _, _ = r.render(cam, family="persistent", want_rgb8=False)
@@ -395,3 +396,26 @@ def test_auto_family_survives_without_room_for_the_queues(monkeypatch):
         frames = [r.render(cam, want_rgb8=False) for _ in range(4)]
     assert all(np.array_equal(rgb.view(np.uint64), want.view(np.uint64)) for rgb, _, _ in frames)
     assert [st["family"] for _, _, st in frames[1:]] == ["persistent"] * 3
+
+
+def test_wavefront_chunked_host_render_overflows_and_recovers(monkeypatch):
+    """Host-buffer renders of the wavefront family run as two interleaved halves whose copies overlap; with a tiny
+    first guess for the queues both halves overflow, the buffers grow, the frame is rendered again — same bits."""
+    flat, camera = load_scene_fixture("refraction")
+    cam = camera.resized(640, 512)  # >= 2^18 pixels: chunked; 512 rows = 32 bands, plus a ragged case below
+    with Renderer(flat) as r:
+        want, want8, wstats = r.render(cam, family="persistent")
+    monkeypatch.setenv("RTGPU_WF_INITIAL_SCALE", "0.02")
+    with Renderer(flat) as r:
+        got, got8, gstats = r.render(cam, family="wavefront")
+        again, again8, astats = r.render(cam, family="wavefront")  # buffers already large enough
+    for rgb, rgb8, st in ((got, got8, gstats), (again, again8, astats)):
+        assert np.array_equal(rgb.view(np.uint64), want.view(np.uint64)) and np.array_equal(rgb8, want8)
+        assert {k: st[k] for k in COUNTERS} == {k: wstats[k] for k in COUNTERS}
+    monkeypatch.delenv("RTGPU_WF_INITIAL_SCALE")
+    flat, camera = load_scene_fixture("cover")
+    cam = camera.resized(700, 411)  # 25 full bands + 11 rows: the last band is partial and belongs to the second half
+    with Renderer(flat) as r:
+        a, a8, _ = r.render(cam, family="persistent")
+        b, b8, _ = r.render(cam, family="wavefront")
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64)) and np.array_equal(a8, b8)
