@@ -198,6 +198,20 @@ def time_oracle(flat, camera, max_depth: int, steps: int, warmup: int, threads: 
     return times, stats.as_dict(), (O.max_threads() if threads <= 0 else threads)
 
 
+def time_oracle_serial_sample(flat, camera, max_depth: int, stride: int = 16):
+    """Serial (1 thread) rate of the oracle on every `stride`-th pixel of the frame — the reference's
+    `--rendering-mode serial`, bounded to about a second of CPU work.  Returns (Mrays/s, pixels sampled)."""
+    from oracle import oracle as O
+
+    n = camera.horizontal_size * camera.vertical_size
+    px = np.arange(0, n, stride, dtype=np.uint64)
+    orc = O.Oracle(flat)
+    t0 = time.perf_counter()
+    _, _, st = orc.render_pixels(camera, px, max_depth=max_depth, threads=1)
+    dt = time.perf_counter() - t0
+    return st["rays"] / dt / 1e6, int(px.size)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -407,9 +421,11 @@ def run_b200(args):
         times, ostats, cores = time_oracle(flat, camera, args.max_depth, steps=3, warmup=1)
         if args.precision == "f64":  # parity mode: the device ray count is integer-equal to the oracle's
             assert ostats["rays"] == rays, (ostats, stats)
+        serial_mrays, serial_px = time_oracle_serial_sample(flat, camera, args.max_depth)
         cpu = {"value": ostats["rays"] / min(times) / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
                "sample": f"the same whole {args.width}x{args.height} frame, best of 3; restated reference (C + OpenMP), not rustc output",
-               "ms_per_frame": min(times) * 1e3}
+               "ms_per_frame": min(times) * 1e3,
+               "serial": {"value": serial_mrays, "unit": "Mrays/s", "cores": 1, "sample": f"every 16th pixel of the frame ({serial_px} pixels), one thread"}}
         line = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": device_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
