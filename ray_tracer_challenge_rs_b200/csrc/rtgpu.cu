@@ -1126,7 +1126,10 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
     // copy the first half while the second one renders — the queues are reused, and the 1 ms copy of a 1080p f64
     // frame is half hidden.  RTGPU_E2E_CHUNKS=1 disables.
     const char* chunks_env = getenv("RTGPU_E2E_CHUNKS");
-    const bool chunked = family == FAMILY_WAVEFRONT && sel.shard_count == 1 && sel.band_rows >= camera->vsize && camera->vsize >= 64 &&
+    // Only for pinned host buffers: a device-to-host copy into pageable memory blocks the submitting thread, so the
+    // second half's kernels would not even be enqueued before the first half's copy has finished.
+    const bool pinned = (!out_rgb || map_rgb) && (!out_rgb8 || map_rgb8);
+    const bool chunked = family == FAMILY_WAVEFRONT && pinned && sel.shard_count == 1 && sel.band_rows >= camera->vsize && camera->vsize >= 64 &&
                          (uint64_t)camera->hsize * camera->vsize >= (1u << 18) && !(chunks_env && chunks_env[0] == '1');
     if (chunked) {
         if (!ctx->copy_stream) {

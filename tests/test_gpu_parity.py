@@ -399,23 +399,38 @@ def test_auto_family_survives_without_room_for_the_queues(monkeypatch):
 
 
 def test_wavefront_chunked_host_render_overflows_and_recovers(monkeypatch):
-    """Host-buffer renders of the wavefront family run as two interleaved halves whose copies overlap; with a tiny
-    first guess for the queues both halves overflow, the buffers grow, the frame is rendered again — same bits."""
+    """Host-buffer renders of the wavefront family into PINNED memory run as two interleaved halves whose copies
+    overlap; with a tiny first guess for the queues both halves overflow, the buffers grow, the frame is rendered
+    again — same bits as the persistent kernel.  Pageable buffers take the single-sequence path."""
+    from ray_tracer_challenge_rs_b200.render import PinnedArray
+
     flat, camera = load_scene_fixture("refraction")
-    cam = camera.resized(640, 512)  # >= 2^18 pixels: chunked; 512 rows = 32 bands, plus a ragged case below
+    cam = camera.resized(640, 512)  # >= 2^18 pixels: chunked; 512 rows = 32 bands; a ragged case follows
+    n = 640 * 512
+    pin, pin8 = PinnedArray((n, 3), np.float64), PinnedArray((n, 3), np.uint8)
     with Renderer(flat) as r:
         want, want8, wstats = r.render(cam, family="persistent")
     monkeypatch.setenv("RTGPU_WF_INITIAL_SCALE", "0.02")
     with Renderer(flat) as r:
-        got, got8, gstats = r.render(cam, family="wavefront")
-        again, again8, astats = r.render(cam, family="wavefront")  # buffers already large enough
-    for rgb, rgb8, st in ((got, got8, gstats), (again, again8, astats)):
-        assert np.array_equal(rgb.view(np.uint64), want.view(np.uint64)) and np.array_equal(rgb8, want8)
-        assert {k: st[k] for k in COUNTERS} == {k: wstats[k] for k in COUNTERS}
+        for _ in range(2):  # the first call enlarges the buffers and renders again, the second finds them large enough
+            pin.array[:] = np.nan
+            pin8.array[:] = 0
+            _, _, st = r.render(cam, family="wavefront", out_rgb=pin.array, out_rgb8=pin8.array)
+            assert np.array_equal(pin.array.view(np.uint64), want.view(np.uint64)) and np.array_equal(pin8.array, want8)
+            assert {k: st[k] for k in COUNTERS} == {k: wstats[k] for k in COUNTERS}
+        pageable, pageable8, _ = r.render(cam, family="wavefront")
+        assert np.array_equal(pageable.view(np.uint64), want.view(np.uint64)) and np.array_equal(pageable8, want8)
+    pin.close()
+    pin8.close()
     monkeypatch.delenv("RTGPU_WF_INITIAL_SCALE")
     flat, camera = load_scene_fixture("cover")
     cam = camera.resized(700, 411)  # 25 full bands + 11 rows: the last band is partial and belongs to the second half
+    n = 700 * 411
+    pin, pin8 = PinnedArray((n, 3), np.float64), PinnedArray((n, 3), np.uint8)
     with Renderer(flat) as r:
         a, a8, _ = r.render(cam, family="persistent")
-        b, b8, _ = r.render(cam, family="wavefront")
-    assert np.array_equal(a.view(np.uint64), b.view(np.uint64)) and np.array_equal(a8, b8)
+        pin.array[:] = np.nan
+        r.render(cam, family="wavefront", out_rgb=pin.array, out_rgb8=pin8.array)
+    assert np.array_equal(a.view(np.uint64), pin.array.view(np.uint64)) and np.array_equal(a8, pin8.array)
+    pin.close()
+    pin8.close()
