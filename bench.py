@@ -156,6 +156,18 @@ def load_workload(args):
     return flat, camera.resized(args.width, args.height)
 
 
+def data_label(args) -> str:
+    return (f"the reference's shipped scenes/{args.scene}.yaml (committed flattened fixture of the YAML), camera resized to "
+            f"{args.width}x{args.height}; no dataset, no random geometry")
+
+
+def quantise_rgb8(rgb: np.ndarray) -> np.ndarray:
+    """Canvas::to_png_file's 8-bit quantisation (canvas.rs:117-123): clamp to [0, 1], * 255, round half away from zero."""
+    v = np.nan_to_num(np.clip(rgb, 0.0, 1.0), nan=0.0) * 255.0
+    r = np.floor(v)
+    return (r + ((v - r) >= 0.5)).astype(np.uint8)
+
+
 def workload_config(args, flat, extra=None) -> dict:
     cfg = {
         "workload": f"{args.scene}.yaml @ {args.width}x{args.height}, {args.precision} {'parity' if args.precision == 'f64' else 'fast'} mode, "
@@ -174,8 +186,20 @@ def workload_config(args, flat, extra=None) -> dict:
 # reference arm: the CPU oracle on all host threads
 
 
+def host_threads() -> int:
+    """Host threads of the CPU arm: every core this process may run on.  Passed to the oracle explicitly —
+    torchrun exports OMP_NUM_THREADS=1 to its workers, which must not shrink the CPU reference to one core."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def time_oracle(flat, camera, max_depth: int, steps: int, warmup: int, threads: int = 0):
     from oracle import oracle as O
+
+    if threads <= 0:
+        threads = host_threads()
 
     orc = O.Oracle(flat)
     n = camera.horizontal_size * camera.vertical_size
@@ -195,7 +219,7 @@ def time_oracle(flat, camera, max_depth: int, steps: int, warmup: int, threads: 
         assert st == 0
         if i >= warmup:
             times.append(t1 - t0)
-    return times, stats.as_dict(), (O.max_threads() if threads <= 0 else threads)
+    return times, stats.as_dict(), threads, rgb
 
 
 def time_oracle_serial_sample(flat, camera, max_depth: int, stride: int = 16):
@@ -217,13 +241,13 @@ def run_reference(args):
     if rank != 0:
         return  # the CPU arm runs once, on rank 0
     flat, camera = load_workload(args)
-    times, stats, cores = time_oracle(flat, camera, args.max_depth, args.steps, args.warmup)
+    times, stats, cores, _ = time_oracle(flat, camera, args.max_depth, args.steps, args.warmup)
     total = sum(times)
     mrays = stats["rays"] * len(times) / total / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic: the reference's cover scene (committed flattened fixture), camera resized",
+        "vs_baseline": None, "dtype": "f64", "data": data_label(args),
         "config": workload_config(args, flat),
         "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port",
                          "sample": f"the whole {args.width}x{args.height} frame, {len(times)} times; restated reference (C + OpenMP, "
@@ -361,6 +385,22 @@ def run_b200(args):
     value = rays * K / (device_ms * 1e-3) / 1e6
     clock_summary = clocks.summary()
 
+    # ---- the frame the ranks just rendered, assembled on rank 0 from their shards (outside every timed region) ----
+    import hashlib
+
+    shard_host = d_out[: my_rows * camera.horizontal_size].cpu().numpy()
+    frame_device = None
+    if world == 1:
+        frame_device = shard_host
+    else:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object((renderer.rows_list(camera, rows), shard_host), gathered, dst=0, group=host_group)
+        if rank == 0:
+            frame_device = np.zeros((camera.vertical_size, camera.horizontal_size, 3), shard_host.dtype)
+            for row_ids, shard in gathered:
+                frame_device[np.asarray(row_ids, dtype=np.int64)] = shard.reshape(len(row_ids), camera.horizontal_size, 3)
+            frame_device = frame_device.reshape(-1, 3)
+
     # ---- end to end through the reference-facing call, host buffers (rank 0 drives all N devices) ----
     n_px = camera.horizontal_size * camera.vertical_size
     e2e = None
@@ -398,6 +438,15 @@ def run_b200(args):
                "call": "rtgpu_render (scene pack + upload, kernel on N devices in 16-row bands, D2H of the full f64 Canvas into pinned host memory)",
                "kernel_ms_max_over_devices": st.kernel_ms, "family": last_family()}
         assert st.as_dict()["rays"] == rays, (st.as_dict(), stats)  # same kernel, same rays as the device-resident leg
+        # ---- pixel identity across N (driver-readable): the N-GPU frames of both legs against a 1-GPU render ----
+        frame_e2e = host_np.copy()
+        opts1 = abi.RtgpuOpts(opts.precision, args.max_depth, 1, 16, family_flag)
+        abi.check(lib, lib.rtgpu_render(C.byref(cscene), C.byref(ccam), C.byref(opts1), host_np.ctypes.data, None, None))
+        sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+        frame_id = {"frame_sha256": sha(frame_device), "frame_sha256_e2e": sha(frame_e2e), "frame_sha256_n1": sha(host_np),
+                    "frame_matches_n1": bool(sha(frame_device) == sha(host_np) and sha(frame_e2e) == sha(host_np)),
+                    "frame_dtype": str(frame_e2e.dtype), "frame_shape": [camera.vertical_size, camera.horizontal_size, 3]}
+        assert frame_id["frame_matches_n1"], frame_id
     host_barrier()
 
     if rank == 0:
@@ -418,21 +467,33 @@ def run_b200(args):
                         f"{n_px * 3 * elem / (device_ms / K * 1e-3) / 1e9 / world:.1f} GB/s per device: HBM is not the bound",
         }
         # ---- CPU baseline beside it (bounded: 3 frames) ----
-        times, ostats, cores = time_oracle(flat, camera, args.max_depth, steps=3, warmup=1)
-        if args.precision == "f64":  # parity mode: the device ray count is integer-equal to the oracle's
-            assert ostats["rays"] == rays, (ostats, stats)
-        serial_mrays, serial_px = time_oracle_serial_sample(flat, camera, args.max_depth)
-        cpu = {"value": ostats["rays"] / min(times) / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-               "sample": f"the same whole {args.width}x{args.height} frame, best of 3; restated reference (C + OpenMP), not rustc output",
-               "ms_per_frame": min(times) * 1e3,
-               "serial": {"value": serial_mrays, "unit": "Mrays/s", "cores": 1, "sample": f"every 16th pixel of the frame ({serial_px} pixels), one thread"}}
+        cpu = None
+        if world == 1:  # the CPU leg runs at N = 1 only (the other N reuse the reference arm the driver runs beside this one)
+            times, ostats, cores, oracle_rgb = time_oracle(flat, camera, args.max_depth, steps=3, warmup=1)
+            serial_mrays, serial_px = time_oracle_serial_sample(flat, camera, args.max_depth)
+            cpu = {"value": ostats["rays"] / min(times) / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                   "sample": f"the same whole {args.width}x{args.height} frame, best of 3; restated reference (C + OpenMP), not rustc output",
+                   "ms_per_frame": min(times) * 1e3,
+                   "serial": {"value": serial_mrays, "unit": "Mrays/s", "cores": 1, "sample": f"every 16th pixel of the frame ({serial_px} pixels), one thread"}}
+            # parity against the oracle's frame of the same run: 8-bit output, and the work counters in parity mode
+            dev8, ora8 = quantise_rgb8(frame_device.astype(np.float64)), quantise_rgb8(oracle_rgb)
+            diff = np.abs(dev8.astype(np.int16) - ora8.astype(np.int16)).max(axis=1)
+            frame_id["rgb8_pixels_differing_from_oracle"] = int((diff > 0).sum())
+            frame_id["rgb8_pixels_beyond_1lsb"] = int((diff > 1).sum())
+            frame_id["oracle_rgb8_sha256"] = sha(ora8)
+            frame_id["rgb8_sha256"] = sha(dev8)
+            if args.precision == "f64":  # parity mode: the device ray count is integer-equal to the oracle's
+                assert ostats["rays"] == rays, (ostats, stats)
+                assert frame_id["rgb8_pixels_differing_from_oracle"] == 0, frame_id
         line = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": device_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": args.precision, "data": "synthetic: the reference's cover scene (committed flattened fixture), camera resized to 1920x1080",
-            "config": workload_config(args, flat, {"parallelism": f"row bands of 4 rows, interleaved over {world} GPU(s); no collective in the data path",
-                                                          "family": family_used, "family_requested": args.family,
-                                                          "family_calibration_frames": CALIBRATION_FRAMES if family is None else 0}),
+            "dtype": args.precision, "data": data_label(args),
+            "config": workload_config(args, flat),  # identical to the reference arm's: the driver compares the two
+            "parallelism": f"row bands of 4 rows, interleaved over {world} GPU(s); no collective in the data path",
+            "family": family_used, "family_requested": args.family,
+            "family_calibration_frames": CALIBRATION_FRAMES if family is None else 0,
+            "frame": frame_id,
             "e2e": e2e, "gpu_launches": launches_per_frame(family_used, args.max_depth) * K * world, "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_summary,
             "rays_per_frame": rays, "ms_per_frame": device_ms / K, "wall_ms_per_step_incl_flush": (t_wall1 - t_wall0) * 1e3 / K,
             "counters": stats,

@@ -38,6 +38,12 @@ namespace rt {
 #ifndef RT_BVH_WATCHDOG
 #define RT_BVH_WATCHDOG 0
 #endif
+#ifndef RT_TMA_STAGE
+#define RT_TMA_STAGE 1  // scene tables -> shared memory by cp.async.bulk + mbarrier (0: plain loads).  Must precede stage_scene.
+#endif
+#ifndef RT_CULL_PREFETCH
+#define RT_CULL_PREFETCH 1
+#endif
 #ifndef RT_CULL
 #define RT_CULL 1  // bounding-sphere pre-test in the intersection loop (exact results either way)
 #endif
@@ -196,6 +202,16 @@ struct SceneView {
             return reinterpret_cast<const int*>(rt_scene_smem + (((size_t)L.n_reals * sizeof(T) + 15) & ~size_t(15)));
         } else {
             return ints;
+        }
+    }
+    // first byte of dynamic shared memory behind the staged tables (SMEM) or the start of it (tables in global memory)
+    RT_DEV unsigned char* scratch() const {
+        extern __shared__ __align__(16) unsigned char rt_scene_smem[];
+        if constexpr (SMEM) {
+            const size_t ints_at = ((size_t)L.n_reals * sizeof(T) + 15) & ~size_t(15);
+            return rt_scene_smem + ((ints_at + (size_t)L.n_ints * sizeof(int) + 15) & ~size_t(15));
+        } else {
+            return rt_scene_smem;
         }
     }
     RT_DEV const T* shape(uint32_t pos) const { return R() + (size_t)pos * SHAPE_REALS; }
@@ -735,11 +751,22 @@ RT_DEV void trace_bvh(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<
 template <typename T, bool FULL, bool SHADOW_EXIT, bool SMEM>
 RT_DEV void trace_unified(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
     const uint32_t n = sv.L.type_begin[NUM_SHAPE_TYPES];
+#if RT_CULL && RT_CULL_PREFETCH
+    // the record of the NEXT shape is loaded one iteration ahead: the pre-test's first operation used to wait for its
+    // own shared-memory load every iteration (ncu: 26 % of the loop's stall samples on that scoreboard)
+    T ncx = T(0), ncy = T(0), ncz = T(0), nr2 = T(0);
+    if (n) load_cull(sv.cull(0), ncx, ncy, ncz, nr2);
+#endif
     for (uint32_t pos = 0; pos < n; ++pos) {
 #if RT_CULL
         {
+#if RT_CULL_PREFETCH
+            const T cx = ncx, cy = ncy, cz = ncz, r2 = nr2;
+            load_cull(sv.cull(pos + 1u < n ? pos + 1u : pos), ncx, ncy, ncz, nr2);
+#else
             T cx, cy, cz, r2;
             load_cull(sv.cull(pos), cx, cy, cz, r2);
+#endif
             const T ocx = cx - ray.o.x, ocy = cy - ray.o.y, ocz = cz - ray.o.z;
             const T bq = fma(ocz, ray.d.z, fma(ocy, ray.d.y, ocx * ray.d.x));
             const T c2 = fma(ocz, ocz, fma(ocy, ocy, ocx * ocx));
@@ -765,6 +792,132 @@ RT_DEV void trace_unified(const SceneView<T, SMEM>& sv, const Ray<T>& ray, Trace
         consume<T, 4>(acc, k, t0, t1, t2, t3, (int)pos, meta);
         // World::is_in_shadow (world.rs:106-111) is an `any`: a lane that has found a blocker is done
         if (SHADOW_EXIT && acc.mode == MODE_SHADOW && acc.best_pos >= 0) break;
+    }
+}
+
+// ---- pair-list trace: World::collect_intersections for the 32 rays of a warp at once --------------------------
+// trace_unified walks the shape list once per lane: after the first bounce the lanes of a warp disagree about which
+// shapes survive the pre-test, so each exact test runs for a handful of lanes (ncu, cover level 5: 8 of 32 threads
+// per instruction inside local_intersect) and every pre-test ends in a data-dependent branch that the next one waits
+// for.  Here the warp works on (ray, shape) PAIRS instead:
+//   A. pre-test: every lane tests ITS ray against a chunk of PAIR_CHUNK shapes, branch-free; survivors are appended to
+//      a warp-private list in shared memory (ballot + prefix count), shape-major, i.e. sorted by shape type;
+//   B. exact test: whenever 32 pairs are waiting (or the shapes are exhausted) lane j takes pair j — some lane's ray,
+//      read from shared memory, against some shape — so the transform and local_intersect run with all 32 lanes and,
+//      pairs being sorted by shape, mostly one shape type per round;
+//   C. consume: the distances go back through shared memory to the lane that owns the ray, which folds them into its
+//      accumulator with the same `consume` as the per-lane loop — (distance, world order) minimum, shadow `any`,
+//      or the container bookkeeping — so the result is the same whatever the order of the pairs.
+// All 32 lanes of a converged warp must call it (idle lanes contribute no pairs).
+#ifndef RT_PAIR_CHUNK
+#define RT_PAIR_CHUNK 4
+#endif
+#ifndef RT_PAIRS_NOINLINE
+#define RT_PAIRS_NOINLINE 0
+#endif
+#if RT_PAIRS_NOINLINE
+#define RT_PAIRS_FN __device__ __noinline__
+#else
+#define RT_PAIRS_FN __device__ __forceinline__
+#endif
+constexpr int PAIR_CHUNK = RT_PAIR_CHUNK;            // shapes pre-tested between two looks at the list
+constexpr int PAIR_RING = PAIR_CHUNK <= 4 ? 256 : 512;  // list capacity (a power of two) >= 31 waiting + PAIR_CHUNK * 32 new ones
+
+template <typename T>
+struct PairScratch {  // one per warp, in dynamic shared memory behind the scene tables
+    T ox[32], oy[32], oz[32], dx[32], dy[32], dz[32];  // the warp's rays
+    T rt[4][32];                                       // distances of the round's pairs, in push order
+    int rn[32];                                        // (shape position << 3) | number of distances
+    unsigned owner[32];                                // per ray: the pair slots of this round that hold its results
+    unsigned list[PAIR_RING + 32];                     // waiting pairs: (shape position << 5) | ray lane; + a dummy slot per lane
+};
+
+template <typename T, bool FULL, bool SHADOW_EXIT, bool SMEM>
+RT_PAIRS_FN void trace_pairs(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<T>& acc, PairScratch<T>* ws) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned below = (1u << lane) - 1u;
+    const uint32_t n = sv.L.type_begin[NUM_SHAPE_TYPES];
+    ws->ox[lane] = ray.o.x; ws->oy[lane] = ray.o.y; ws->oz[lane] = ray.o.z;
+    ws->dx[lane] = ray.d.x; ws->dy[lane] = ray.d.y; ws->dz[lane] = ray.d.z;
+    __syncwarp();
+    bool live = acc.mode != MODE_IDLE;
+    const bool behind_counts = acc.mode == MODE_CONTAINER;  // negative distances matter to the container walk only
+    uint32_t pos = 0, head = 0, tail = 0;
+    for (;;) {
+        const uint32_t avail = tail - head;
+        if (avail < 32u && pos < n) {
+            // ---- A: pre-test PAIR_CHUNK shapes (see trace_unified for the test itself) ----
+            // Branch-free on purpose: no test depends on another's outcome, so the loads of the whole chunk can be
+            // issued first and the chains interleave.  Positions past the end re-test the last shape and are masked.
+#pragma unroll
+            for (int j = 0; j < PAIR_CHUNK; ++j) {
+                const uint32_t p = min(pos + (uint32_t)j, n - 1u);
+                bool pass = live & (pos + (uint32_t)j < n);
+#if RT_CULL
+                T cx, cy, cz, r2;
+                load_cull(sv.cull(p), cx, cy, cz, r2);
+                const T ocx = cx - ray.o.x, ocy = cy - ray.o.y, ocz = cz - ray.o.z;
+                const T bq = fma(ocz, ray.d.z, fma(ocy, ray.d.y, ocx * ray.d.x));
+                const T c2 = fma(ocz, ocz, fma(ocy, ocy, ocx * ocx));
+                const T ex = fma(c2, sv.cull_shrink(), -r2);
+                const bool outside = ex > T(0), behind = bq < T(0), misses = ex * acc.dir_sq > bq * bq;
+                pass = pass & !(outside & ((behind & !behind_counts) | misses));
+#endif
+                const unsigned b = __ballot_sync(0xffffffffu, pass);
+                // losers write to a private dummy slot behind the ring: no branch around the store
+                const uint32_t slot = pass ? ((tail + (uint32_t)__popc(b & below)) & (PAIR_RING - 1)) : (uint32_t)PAIR_RING + lane;
+                ws->list[slot] = (p << 5) | lane;
+                tail += (uint32_t)__popc(b);
+            }
+            pos += PAIR_CHUNK;
+            continue;
+        }
+        if (avail == 0u) break;
+        // ---- B: one round of exact tests, lane j on pair head + j ----
+        const uint32_t cnt = avail < 32u ? avail : 32u;
+        __syncwarp();  // the list entries of this round are visible
+        if (lane < cnt) {
+            const unsigned e = ws->list[(head + lane) & (PAIR_RING - 1)];
+            const uint32_t sp = e >> 5, r = e & 31u;
+            Ray<T> wr;
+            wr.o = mk<T>(ws->ox[r], ws->oy[r], ws->oz[r]);
+            wr.d = mk<T>(ws->dx[r], ws->dy[r], ws->dz[r]);
+            const T* g = sv.shape(sp);
+            const int4 meta = sv.shape_meta(sp);
+            Ray<T> local;  // ray.rs:45-49
+            local.o = mat_point(g, wr.o);
+            local.d = mat_vector(g, wr.d);
+            T t0 = T(0), t1 = T(0), t2 = T(0), t3 = T(0);
+            int k = 0;
+            switch ((meta.z >> FLAG_TYPE_SHIFT) & 7) {
+            case 0: k = local_intersect<T, 0>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
+            case 1: k = local_intersect<T, 1>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
+            case 2: k = local_intersect<T, 2>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
+            case 3: if (FULL) k = local_intersect<T, 3>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
+            case 4: if (FULL) k = local_intersect<T, 4>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
+            default: if (FULL) k = local_intersect<T, 5>(local, g, meta.z, sv.triangle(sp), t0, t1, t2, t3); break;
+            }
+            if (k > 0) {
+                ws->rt[0][lane] = t0; ws->rt[1][lane] = t1; ws->rt[2][lane] = t2; ws->rt[3][lane] = t3;
+                ws->rn[lane] = (int)((sp << 3) | (uint32_t)k);
+                atomicOr(&ws->owner[r], 1u << lane);
+            }
+        }
+        head += cnt;
+        __syncwarp();
+        // ---- C: every lane folds the results of ITS ray into its accumulator ----
+        unsigned mine = ws->owner[lane];
+        if (mine) ws->owner[lane] = 0u;
+        while (mine) {
+            const int j = __ffs((int)mine) - 1;
+            mine &= mine - 1u;
+            const int rn = ws->rn[j];
+            const uint32_t sp = (uint32_t)rn >> 3;
+            consume<T, 4>(acc, rn & 7, ws->rt[0][j], ws->rt[1][j], ws->rt[2][j], ws->rt[3][j], (int)sp, sv.shape_meta(sp));
+        }
+        // World::is_in_shadow (world.rs:106-111) is an `any`: a lane that has found a blocker adds no more pairs
+        if (SHADOW_EXIT && acc.mode == MODE_SHADOW && acc.best_pos >= 0) live = false;
+        __syncwarp();  // results consumed before the next round overwrites them
     }
 }
 
@@ -856,11 +1009,6 @@ enum : int { ST_FETCH = 0, ST_RADIANCE = 1, ST_CONTAINER = 2, ST_SHADOW = 3, ST_
 #ifndef RT_MIN_BLOCKS_PER_SM
 #define RT_MIN_BLOCKS_PER_SM 4
 #endif
-
-#ifndef RT_TMA_STAGE
-#define RT_TMA_STAGE 1  // scene tables -> shared memory by cp.async.bulk + mbarrier (0: plain loads)
-#endif
-
 
 #ifndef RT_PHASE_SYNC
 #define RT_PHASE_SYNC 0
@@ -1007,7 +1155,9 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
         acc.mode = (state == ST_RADIANCE) ? MODE_RADIANCE : (state == ST_SHADOW) ? MODE_SHADOW : (state == ST_CONTAINER) ? MODE_CONTAINER : MODE_IDLE;
         acc.best_t = (state == ST_SHADOW) ? shadow_distance : Real<T>::max();
         acc.dir_sq = fma(ray.d.z, ray.d.z, fma(ray.d.y, ray.d.y, ray.d.x * ray.d.x));
-        acc.best_orig = 0x7fffffff;
+        // intersection.rs:77-79: a blocker needs t < light distance, strictly: with the seed order -1 the
+        // `t == best_t && order < best_orig` arm of consume() can never accept a hit AT the light's distance
+        acc.best_orig = (state == ST_SHADOW) ? -1 : 0x7fffffff;
         acc.best_pos = -1;
         if (state == ST_CONTAINER) {  // the container bookkeeping lives in local memory: only touch it when it is used
             acc.c->t_hit = t_hit;

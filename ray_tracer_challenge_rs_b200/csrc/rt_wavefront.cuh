@@ -106,7 +106,8 @@ RT_DEV void wf_reset_acc(TraceAcc<T>& acc, int mode, const Ray<T>& ray, T best_t
     acc.mode = mode;
     acc.best_t = best_t;
     acc.dir_sq = fma(ray.d.z, ray.d.z, fma(ray.d.y, ray.d.y, ray.d.x * ray.d.x));
-    acc.best_orig = 0x7fffffff;
+    // strict `t < light distance` for shadow queries (intersection.rs:77-79): see render_kernel
+    acc.best_orig = (mode == MODE_SHADOW) ? -1 : 0x7fffffff;
     acc.best_pos = -1;
     if (mode == MODE_CONTAINER) {  // the container bookkeeping lives in local memory: only touch it when it is used
         acc.c->t_hit = T(0);
@@ -118,10 +119,19 @@ RT_DEV void wf_reset_acc(TraceAcc<T>& acc, int mode, const Ray<T>& ray, T best_t
     }
 }
 
+#ifndef RT_WF_PAIRS
+#define RT_WF_PAIRS 0  // 1: the uniform shape list is traced as compacted (ray, shape) pairs (trace_pairs; measured slower, profiles/r2_notes.md); 0: per-lane loop
+#endif
+
+// Called by all 32 lanes of a converged warp.
 template <typename T, bool FULL, bool BVH, bool SMEM>
-RT_DEV void wf_trace(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
-    if (acc.mode != MODE_IDLE) trace_unified<T, FULL, true>(sv, ray, acc);
-    if (BVH) trace_bvh<T, FULL>(sv, ray, acc);  // warp votes inside: every lane takes part
+RT_DEV void wf_trace(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<T>& acc, PairScratch<T>* ws) {
+    if (RT_WF_PAIRS && !BVH) {
+        trace_pairs<T, FULL, true>(sv, ray, acc, ws);
+    } else {
+        if (acc.mode != MODE_IDLE) trace_unified<T, FULL, true>(sv, ray, acc);  // BVH scenes: the unbounded shapes
+        if (BVH) trace_bvh<T, FULL>(sv, ray, acc);  // warp votes inside: every lane takes part
+    }
 }
 
 template <typename T, bool FULL, bool BVH, bool SMEM>
@@ -155,6 +165,12 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
     unsigned int c_primary = 0, c_shadow = 0, c_reflect = 0, c_refract = 0, c_nodes = 0;
     if constexpr (SMEM) {
         if (n_items) stage_scene<T>(layout, g_reals, g_ints);  // (uniform over the grid) nothing queued: nothing to stage
+    }
+    // the warp's scratch for the pair-list trace, behind the staged tables
+    PairScratch<T>* const ws = reinterpret_cast<PairScratch<T>*>(sv.scratch()) + (threadIdx.x >> 5);
+    if (RT_WF_PAIRS && !BVH) {
+        ws->owner[lane] = 0u;
+        __syncwarp();
     }
 
     for (;;) {
@@ -280,7 +296,7 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                 acc.c->t_hit = t_hit;
                 acc.c->hit_class = sv.shape_meta((uint32_t)hit_pos).w;
             }
-            if (__any_sync(0xffffffffu, mode != MODE_IDLE)) wf_trace<T, FULL, BVH>(sv, tray, acc);
+            if (__any_sync(0xffffffffu, mode != MODE_IDLE)) wf_trace<T, FULL, BVH>(sv, tray, acc, ws);
 
             if (phase == 0) {
                 // ---- World::internal_color_at (world.rs:70-86): the hit, the node, prepare_computations ----

@@ -33,6 +33,19 @@ def _opts(precision: str = "f64", max_depth: int = World.MAX_REFLECTION_ITERATIO
 FAMILY_NAMES = ("persistent", "wavefront")
 
 
+def _check_out(arr, dtype, size: int, name: str) -> None:
+    """The library writes `size` elements of `dtype` through the raw pointer: anything else would overflow the
+    caller's buffer or be filled with reinterpreted values."""
+    if arr is None:
+        return
+    if not isinstance(arr, np.ndarray) or arr.dtype != np.dtype(dtype):
+        raise ValueError(f"{name} must be a numpy array of dtype {np.dtype(dtype).name} (got {getattr(arr, 'dtype', type(arr))})")
+    if not arr.flags["C_CONTIGUOUS"] or not arr.flags["WRITEABLE"]:
+        raise ValueError(f"{name} must be C-contiguous and writeable")
+    if arr.size != size:
+        raise ValueError(f"{name} must hold exactly {size} elements (full frame x 3), got {arr.size}")
+
+
 def last_family() -> str:
     """The kernel family this thread's most recent render ran (``rtgpu_last_family``)."""
     return FAMILY_NAMES[int(abi.load_library().rtgpu_last_family())]
@@ -116,6 +129,14 @@ class Renderer:
         r = abi.RtgpuRows(*(rows or (0, 0, 1)))
         return int(self._lib.rtgpu_rows_count(C.byref(r), camera.vertical_size))
 
+    def rows_list(self, camera: Camera, rows: Optional[Tuple[int, int, int]]):
+        """Image rows of the selection, in the order the compact output of a shard holds them (``rtgpu_rows_list``)."""
+        r = abi.RtgpuRows(*(rows or (0, 0, 1)))
+        n = self.rows_count(camera, rows)
+        out = (C.c_uint32 * max(n, 1))()
+        self._lib.rtgpu_rows_list(C.byref(r), camera.vertical_size, out, n)
+        return [int(out[i]) for i in range(n)]
+
     def render(
         self,
         camera: Camera,
@@ -136,6 +157,8 @@ class Renderer:
             out_rgb = np.zeros((n, 3), dtype)
         if out_rgb8 is None and want_rgb8:
             out_rgb8 = np.zeros((n, 3), np.uint8)
+        _check_out(out_rgb, dtype, n * 3, "out_rgb")
+        _check_out(out_rgb8, np.uint8, n * 3, "out_rgb8")
         ccam = camera_to_c(camera)
         opts = _opts(precision, max_depth, family=family)
         r = abi.RtgpuRows(*(rows or (0, 0, 1)))
