@@ -42,7 +42,7 @@ namespace rt {
 #define RT_TMA_STAGE 1  // scene tables -> shared memory by cp.async.bulk + mbarrier (0: plain loads).  Must precede stage_scene.
 #endif
 #ifndef RT_CULL_PREFETCH
-#define RT_CULL_PREFETCH 1
+#define RT_CULL_PREFETCH 0
 #endif
 #ifndef RT_CULL
 #define RT_CULL 1  // bounding-sphere pre-test in the intersection loop (exact results either way)

@@ -40,11 +40,12 @@ template <typename T>
 struct WfRay {
     T ox, oy, oz, dx, dy, dz;
     T t;         // hit distance (Intersections::hit, intersections.rs:13-18)
-    T k;         // the parent's reflectiveness (slot 0) / transparency (slot 1): scales the colour sent back
     int pos;     // sorted position of the hit shape
+    int pad;
+    // the tail is read again when the node is finished (it is not kept in registers across the node's traces)
+    T k;         // the parent's reflectiveness (slot 0) / transparency (slot 1): scales the colour sent back
     int parent;  // node that spawned the ray
     int slot;    // 0: its reflected colour, 1: its refracted colour
-    int pad;
 };
 
 template <typename T>
@@ -78,7 +79,7 @@ struct WfCounts {
 #define RT_WF_THREADS 128
 #endif
 #ifndef RT_WF_MIN_BLOCKS
-#define RT_WF_MIN_BLOCKS 4
+#define RT_WF_MIN_BLOCKS 6
 #endif
 
 template <typename T>
@@ -118,6 +119,8 @@ RT_DEV void wf_reset_acc(TraceAcc<T>& acc, int mode, const Ray<T>& ray, T best_t
         acc.c->all_orig = acc.c->excl_orig = 0;
     }
 }
+
+constexpr int WF_PARK_REALS = 19;  // per-thread node state parked in shared memory (wf_level_kernel, PK_*)
 
 #ifndef RT_WF_PAIRS
 #define RT_WF_PAIRS 0  // 1: the uniform shape list is traced as compacted (ray, shape) pairs (trace_pairs; measured slower, profiles/r2_notes.md); 0: per-lane loop
@@ -162,12 +165,19 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
     const unsigned n_items = level == 0 ? tiles_x * tiles_y * (TILE_W * TILE_H) : front_padded + n_back;
     const int n_lights = (int)layout.n_lights;
     const int remaining = (int)cam.max_depth - level;
-    unsigned int c_primary = 0, c_shadow = 0, c_reflect = 0, c_refract = 0, c_nodes = 0;
+    // work counters of the warp (primary, reflect, refract, nodes; shadow rays = nodes x lights): in shared memory, fed
+    // by ballots once per work item, instead of five registers per lane that would be live across every trace
+    __shared__ unsigned s_count[RT_WF_THREADS / 32][4];
+    unsigned* const my_count = s_count[threadIdx.x >> 5];
+    if (lane < 4u) my_count[lane] = 0u;
+    __syncwarp();
     if constexpr (SMEM) {
         if (n_items) stage_scene<T>(layout, g_reals, g_ints);  // (uniform over the grid) nothing queued: nothing to stage
     }
-    // the warp's scratch for the pair-list trace, behind the staged tables
+    // behind the staged tables: the warps' scratch for the pair-list trace (if compiled in), then WF_PARK_REALS columns
+    // of per-thread node state
     PairScratch<T>* const ws = reinterpret_cast<PairScratch<T>*>(sv.scratch()) + (threadIdx.x >> 5);
+    T* const park = reinterpret_cast<T*>(sv.scratch() + ((RT_WF_PAIRS && !BVH) ? (RT_WF_THREADS / 32) * sizeof(PairScratch<T>) : 0)) + threadIdx.x;
     if (RT_WF_PAIRS && !BVH) {
         ws->owner[lane] = 0u;
         __syncwarp();
@@ -194,14 +204,18 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
 #endif
 
         // ---- the radiance ray of this work item -------------------------------------------------
+        // The kernel is register-bound (occupancy) and a node's state would be live across every trace of the node,
+        // so the state lives in SHARED memory, one column per thread (PK(i)): each phase loads what it needs before
+        // its trace and again after it.  P is the ray's origin until the hit is known and the hit POINT afterwards, D
+        // the ray's direction; over / under points, the eye and reflect vectors and the refracted direction are
+        // recomputed from (P, D, normal) where they are used — the same expressions as before, hence the same bits.
+#define PK(i) park[(i) * RT_WF_THREADS]
+        enum { PK_SURFACE = 0, PK_BASE = 3, PK_P = 6, PK_D = 9, PK_NORMAL = 12, PK_T_HIT = 15, PK_REFLECTANCE = 16, PK_REFR_A = 17, PK_REFR_N = 18 };
+        static_assert(PK_REFR_N < WF_PARK_REALS, "WF_PARK_REALS too small");
         bool active = item < n_items;
-        Ray<T> ray;
-        ray.o = mk<T>(T(0), T(0), T(0));
-        ray.d = mk<T>(T(0), T(0), T(1));
-        int parent = -1, slot = 0;
-        size_t out_index = 0;
-        int queued_pos = -1;
-        T queued_t = T(0), k_parent = T(1);
+        unsigned out_index = 0;
+        int hit_pos = -1;      // deeper levels: the hit their parent's launch found
+        unsigned q_index = 0;  // deeper levels: where the item sits in the input queue
         if (level == 0) {
             if (active) {
                 const uint32_t tile = item / (TILE_W * TILE_H), in = item % (TILE_W * TILE_H);
@@ -217,22 +231,20 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                     T world_y = cam.half_height - offset_y;
                     V3<T> pixel = mat_point(cam.inv, mk<T>(world_x, world_y, T(-1)));
                     V3<T> origin = ld3(cam.origin);
-                    ray.o = origin;
-                    ray.d = normalized(pixel - origin);
-                    out_index = (size_t)(cam.out_full_frame ? y : k) * cam.hsize + x;
-                    ++c_primary;
+                    const V3<T> d = normalized(pixel - origin);
+                    PK(PK_P + 0) = origin.x; PK(PK_P + 1) = origin.y; PK(PK_P + 2) = origin.z;
+                    PK(PK_D + 0) = d.x; PK(PK_D + 1) = d.y; PK(PK_D + 2) = d.z;
+                    out_index = (cam.out_full_frame ? y : k) * cam.hsize + x;
                 }
             }
         } else if (active && (item < n_front || item >= front_padded)) {
             // the parent's launch already traced this ray and only queued it because it hit
-            const WfRay<T> r = rays_in[item < n_front ? item : cap_rays - 1u - (item - front_padded)];
-            ray.o = mk<T>(r.ox, r.oy, r.oz);
-            ray.d = mk<T>(r.dx, r.dy, r.dz);
-            parent = r.parent;
-            slot = r.slot;
-            k_parent = r.k;
-            queued_pos = r.pos;
-            queued_t = r.t;
+            q_index = item < n_front ? item : cap_rays - 1u - (item - front_padded);
+            const WfRay<T>& r = rays_in[q_index];
+            PK(PK_P + 0) = r.ox; PK(PK_P + 1) = r.oy; PK(PK_P + 2) = r.oz;
+            PK(PK_D + 0) = r.dx; PK(PK_D + 1) = r.dy; PK(PK_D + 2) = r.dz;
+            PK(PK_T_HIT) = r.t;
+            hit_pos = r.pos;
         } else {
             active = false;  // padding between the two ends of the queue
         }
@@ -240,10 +252,9 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
         // per-node state, filled phase by phase
         bool alive = false, need_containers = false;
         unsigned node_index = 0;
-        V3<T> over = ray.o, under = ray.o, normal = ray.d, eye = ray.d, reflect_dir = ray.d, refr_d = ray.d, base = ray.d;
-        V3<T> surface = mk<T>(T(0), T(0), T(0));
-        int hit_pos = 0, hit_material = 0, flags = 0;
-        T t_hit = T(0), reflectance = T(0), k_reflect = T(0), k_transparent = T(0);
+        PK(PK_SURFACE + 0) = T(0); PK(PK_SURFACE + 1) = T(0); PK(PK_SURFACE + 2) = T(0);  // Color::BLACK
+        int hit_material = 0, flags = 0;
+        const bool is_primary = level == 0 && active;
 
         // Every query of a node goes through ONE copy of the intersection code: the phases below only differ in
         // the ray they set up before it and in what they do with the answer after it.  (Five inlined copies
@@ -258,33 +269,45 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
 #if RT_WF_SYNC
             __syncthreads();
 #endif
-            Ray<T> tray = ray;
+            Ray<T> tray;
+            tray.o = mk<T>(T(0), T(0), T(0));
+            tray.d = mk<T>(T(0), T(0), T(1));
             int mode = MODE_IDLE;
             T seed = Real<T>::max();
             const int light = phase - 2;
             const int child = phase - 2 - n_lights;
             bool spawn = false;
-            if (phase == 0) {
-                if (level == 0 && active) mode = MODE_RADIANCE;
-            } else if (phase == 1) {
-                if (need_containers) mode = MODE_CONTAINER;
-            } else if (child < 0) {
-                if (alive) {  // World::is_in_shadow, world.rs:98-112
-                    Normalized<T> nl = normalize_full(ld3(sv.light((uint32_t)light)) - over);
-                    tray.o = over;
-                    tray.d = nl.v;
-                    seed = nl.magnitude;
-                    mode = MODE_SHADOW;
-                    ++c_shadow;
+            if (phase <= 1) {
+                // phase 0: the camera ray; phase 1: the same ray again for the containers (P is still its origin)
+                if (phase == 0 ? (level == 0 && active) : need_containers) {
+                    tray.o = mk<T>(PK(PK_P + 0), PK(PK_P + 1), PK(PK_P + 2));
+                    tray.d = mk<T>(PK(PK_D + 0), PK(PK_D + 1), PK(PK_D + 2));
+                    mode = phase == 0 ? MODE_RADIANCE : MODE_CONTAINER;
                 }
             } else {
-                spawn = alive && (flags & (child == 0 ? FR_REFLECT : FR_REFRACT));
+                spawn = alive && (child < 0 || (flags & (child == 0 ? FR_REFLECT : FR_REFRACT)));
                 if (spawn) {
-                    tray.o = child == 0 ? over : under;  // world.rs:124 / world.rs:152
-                    tray.d = child == 0 ? reflect_dir : refr_d;
-                    mode = MODE_RADIANCE;
-                    if (child == 0) ++c_reflect;
-                    else ++c_refract;
+                    const V3<T> P = mk<T>(PK(PK_P + 0), PK(PK_P + 1), PK(PK_P + 2));
+                    const V3<T> normal = mk<T>(PK(PK_NORMAL + 0), PK(PK_NORMAL + 1), PK(PK_NORMAL + 2));
+                    const V3<T> off = normal * Real<T>::offset_eps();  // computed_hit.rs:33-34
+                    if (child < 0) {  // World::is_in_shadow, world.rs:98-112
+                        const V3<T> over = P + off;
+                        Normalized<T> nl = normalize_full(ld3(sv.light((uint32_t)light)) - over);
+                        tray.o = over;
+                        tray.d = nl.v;
+                        seed = nl.magnitude;
+                        mode = MODE_SHADOW;
+                    } else {
+                        const V3<T> D = mk<T>(PK(PK_D + 0), PK(PK_D + 1), PK(PK_D + 2));
+                        if (child == 0) {  // world.rs:124, intersection.rs:31
+                            tray.o = P + off;
+                            tray.d = reflect(D, normal);
+                        } else {  // world.rs:150-152
+                            tray.o = P - off;
+                            tray.d = (normal * PK(PK_REFR_A)) - (neg(D) * PK(PK_REFR_N));
+                        }
+                        mode = MODE_RADIANCE;
+                    }
                 }
             }
 
@@ -293,36 +316,32 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
             acc.c = RT_ACC_SPLIT ? &cacc : acc_store(acc);
             wf_reset_acc(acc, mode, tray, seed);
             if (phase == 1 && need_containers) {
-                acc.c->t_hit = t_hit;
+                acc.c->t_hit = PK(PK_T_HIT);
                 acc.c->hit_class = sv.shape_meta((uint32_t)hit_pos).w;
             }
             if (__any_sync(0xffffffffu, mode != MODE_IDLE)) wf_trace<T, FULL, BVH>(sv, tray, acc, ws);
+            asm volatile("" ::: "memory");  // parked state is loaded again below, not carried in registers across the trace
 
             if (phase == 0) {
                 // ---- World::internal_color_at (world.rs:70-86): the hit, the node, prepare_computations ----
-                if (level != 0 && active) {
-                    acc.best_pos = queued_pos;
-                    acc.best_t = queued_t;
-                }
-                const bool hit = active && acc.best_pos >= 0;
-                if (level == 0 && active && !hit) wf_store_pixel(out_rgb, out_rgb8, out_index, mk<T>(T(0), T(0), T(0)));  // World::DEFAULT_COLOR
-                alive = hit;
-                if (alive) {  // intersection.rs:21-31, computed_hit.rs:33-34
-                    ++c_nodes;
+                if (level == 0) {
                     hit_pos = acc.best_pos;
-                    t_hit = acc.best_t;
+                    PK(PK_T_HIT) = acc.best_t;
+                }
+                const bool hit = active && hit_pos >= 0;
+                if (level == 0 && active && !hit) wf_store_pixel(out_rgb, out_rgb8, (size_t)out_index, mk<T>(T(0), T(0), T(0)));  // World::DEFAULT_COLOR
+                alive = hit;
+                if (alive) {  // intersection.rs:21-31
                     const T* g = sv.shape((uint32_t)hit_pos);
                     const int4 meta = sv.shape_meta((uint32_t)hit_pos);
                     hit_material = meta.y;
-                    V3<T> point = ray.o + ray.d * t_hit;
+                    const V3<T> P = mk<T>(PK(PK_P + 0), PK(PK_P + 1), PK(PK_P + 2)), D = mk<T>(PK(PK_D + 0), PK(PK_D + 1), PK(PK_D + 2));
+                    V3<T> point = P + D * PK(PK_T_HIT);
                     V3<T> local_point = mat_point(g, point);  // shape.rs:22-27
                     V3<T> local_normal = local_normal_at(sv, (uint32_t)hit_pos, (meta.z >> FLAG_TYPE_SHIFT) & 7, g, local_point);
-                    normal = normalized(mat_transposed_vector(g, local_normal));
-                    eye = neg(ray.d);
-                    if (dot(normal, eye) < T(0)) normal = neg(normal);
-                    reflect_dir = reflect(ray.d, normal);  // intersection.rs:31
-                    over = point + (normal * Real<T>::offset_eps());
-                    under = point - (normal * Real<T>::offset_eps());
+                    V3<T> normal = normalized(mat_transposed_vector(g, local_normal));
+                    if (dot(normal, neg(D)) < T(0)) normal = neg(normal);
+                    PK(PK_NORMAL + 0) = normal.x; PK(PK_NORMAL + 1) = normal.y; PK(PK_NORMAL + 2) = normal.z;
                     // n1 / n2 only feed refracted_color and Schlick, both irrelevant without iterations left
                     need_containers = sv.material((uint32_t)hit_material)[MAT_TRANSPARENCY] != T(0) && remaining > 0;
                 }
@@ -338,8 +357,12 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                 }
                 if (alive) {
                     const T* m = sv.material((uint32_t)hit_material);
-                    k_reflect = m[MAT_REFLECTIVENESS];
-                    k_transparent = m[MAT_TRANSPARENCY];
+                    const V3<T> D = mk<T>(PK(PK_D + 0), PK(PK_D + 1), PK(PK_D + 2));
+                    const V3<T> normal = mk<T>(PK(PK_NORMAL + 0), PK(PK_NORMAL + 1), PK(PK_NORMAL + 2));
+                    // from here on P is the hit point (the container query above was the last user of the origin)
+                    const V3<T> P = mk<T>(PK(PK_P + 0), PK(PK_P + 1), PK(PK_P + 2)) + D * PK(PK_T_HIT);
+                    PK(PK_P + 0) = P.x; PK(PK_P + 1) = P.y; PK(PK_P + 2) = P.z;
+                    const V3<T> eye = neg(D);
                     if (remaining > 0 && m[MAT_REFLECTIVENESS] != T(0)) flags |= FR_REFLECT;  // world.rs:120
                     const T cos_i = dot(eye, normal);
                     if (remaining > 0 && m[MAT_TRANSPARENCY] != T(0)) {  // world.rs:136-154
@@ -347,7 +370,8 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                         T sin2_t = sq(n_ratio) * (T(1) - sq(cos_i));
                         if (!(sin2_t > T(1))) {
                             T cos_t = sqrt(T(1) - sin2_t);
-                            refr_d = (normal * fma(n_ratio, cos_i, -cos_t)) - (eye * n_ratio);
+                            PK(PK_REFR_A) = fma(n_ratio, cos_i, -cos_t);  // refracted direction = normal * a - eye * n_ratio (world.rs:150)
+                            PK(PK_REFR_N) = n_ratio;
                             flags |= FR_REFRACT;
                         }
                     }
@@ -355,6 +379,7 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                         flags |= FR_SCHLICK;
                         T c = cos_i;  // ComputedHit::schlicks_approximation, computed_hit.rs:50-68
                         bool total = false;
+                        T reflectance;
                         if (n1 > n2) {
                             T ratio = n1 / n2;
                             T sin2_t = sq(ratio) * (T(1) - sq(c));
@@ -369,16 +394,20 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                             T x5 = x * ((x * x) * (x * x));  // powi(5)
                             reflectance = fma(T(1) - r0, x5, r0);
                         }
+                        PK(PK_REFLECTANCE) = reflectance;
                     }
                     // Material::resolve_color, material.rs:75-80
                     const int pat = sv.material_pattern((uint32_t)hit_material);
+                    V3<T> base;
                     if (pat >= 0) {
+                        const V3<T> over = P + (normal * Real<T>::offset_eps());
                         V3<T> object_point = mat_point(sv.shape((uint32_t)hit_pos), over);  // pattern.rs:10-14
                         V3<T> pattern_point = mat_point(sv.pattern((uint32_t)pat) + 6, object_point);
                         base = pattern_color_at(sv, pat, pattern_point);
                     } else {
                         base = ld3(m);
                     }
+                    PK(PK_BASE + 0) = base.x; PK(PK_BASE + 1) = base.y; PK(PK_BASE + 2) = base.z;
                 }
             } else if (child < 0) {
                 // ---- Material::lighting, material.rs:53-114, at over_point (material.rs:116-130) ------------
@@ -386,6 +415,8 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                     const T* lt = sv.light((uint32_t)light);
                     const T* m = sv.material((uint32_t)hit_material);
                     V3<T> intensity = ld3(lt + 3);
+                    const V3<T> base = mk<T>(PK(PK_BASE + 0), PK(PK_BASE + 1), PK(PK_BASE + 2));
+                    const V3<T> normal = mk<T>(PK(PK_NORMAL + 0), PK(PK_NORMAL + 1), PK(PK_NORMAL + 2));
                     V3<T> effective = hadamard(base, intensity);
                     V3<T> ambient = effective * m[MAT_AMBIENT];
                     V3<T> lit = ambient;
@@ -395,7 +426,7 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                         if (!(ldn < T(0))) {
                             V3<T> diffuse = (effective * m[MAT_DIFFUSE]) * ldn;
                             V3<T> refl = reflect(neg(light_dir), normal);
-                            T rde = dot(refl, eye);
+                            T rde = dot(refl, neg(mk<T>(PK(PK_D + 0), PK(PK_D + 1), PK(PK_D + 2))));
                             if (rde <= T(0) || m[MAT_SPECULAR] == T(0)) {  // see render_kernel: an exact zero term
                                 lit = ambient + diffuse;
                             } else {
@@ -405,11 +436,12 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                             }
                         }
                     }
-                    surface = surface + lit;  // fold(Color::BLACK, Color::add)
+                    // fold(Color::BLACK, Color::add)
+                    PK(PK_SURFACE + 0) += lit.x; PK(PK_SURFACE + 1) += lit.y; PK(PK_SURFACE + 2) += lit.z;
                 }
             } else {
                 // ---- a child that hit something becomes a work item of the next level -----------------------
-                const bool child_hit = spawn && acc.best_pos >= 0;
+                const bool child_hit = spawn && acc.best_pos >= 0;  // (spawn: this lane traced a child in this phase)
                 // which end of the next queue: does the child's hit need the container / refraction phases?
                 const bool glass = child_hit && sv.material((uint32_t)sv.shape_meta((uint32_t)acc.best_pos).y)[MAT_TRANSPARENCY] != T(0);
                 const unsigned queued_front = __ballot_sync(0xffffffffu, child_hit && !glass);
@@ -433,7 +465,7 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                             r.ox = tray.o.x; r.oy = tray.o.y; r.oz = tray.o.z;
                             r.dx = tray.d.x; r.dy = tray.d.y; r.dz = tray.d.z;
                             r.t = acc.best_t;
-                            r.k = child == 0 ? k_reflect : k_transparent;
+                            r.k = sv.material((uint32_t)hit_material)[child == 0 ? MAT_REFLECTIVENESS : MAT_TRANSPARENCY];
                             r.pos = acc.best_pos;
                             r.parent = (int)node_index;
                             r.slot = child;
@@ -456,6 +488,16 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                     node_base = __shfl_sync(0xffffffffu, node_base, 0);
                     node_index = node_base + __popc(records & ((1u << lane) - 1u));
                 }
+                const V3<T> surface = mk<T>(PK(PK_SURFACE + 0), PK(PK_SURFACE + 1), PK(PK_SURFACE + 2));
+                // whose child this node is: read back from the queue entry (level 0: a pixel's root)
+                int parent = -1, slot = 0;
+                T k_parent = T(1);
+                if (level > 0 && alive) {
+                    const WfRay<T>& r = rays_in[q_index];
+                    k_parent = r.k;
+                    parent = r.parent;
+                    slot = r.slot;
+                }
                 if (interior && node_index >= cap_nodes) {
                     counts->overflow = 1u;
                     flags &= ~(FR_REFLECT | FR_REFRACT);  // no record, no children: the frame is re-rendered anyway
@@ -463,10 +505,10 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                     WfNode<T> nd;
                     nd.parent = parent;
                     nd.slot = slot;
-                    nd.pixel = (unsigned)out_index;
+                    nd.pixel = out_index;
                     nd.flags = flags & FR_SCHLICK;
                     nd.k_parent = k_parent;
-                    nd.reflectance = reflectance;
+                    nd.reflectance = (flags & FR_SCHLICK) ? PK(PK_REFLECTANCE) : T(0);
                     nd.surface[0] = surface.x; nd.surface[1] = surface.y; nd.surface[2] = surface.z;
                     nd.reflected[0] = nd.reflected[1] = nd.reflected[2] = T(0);  // world.rs:121
                     nd.refracted[0] = nd.refracted[1] = nd.refracted[2] = T(0);  // world.rs:137,146
@@ -474,7 +516,7 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                 } else if (alive) {
                     // world.rs:59-66 with black children: (surface + 0) + 0 — and 0 * reflectance is 0 too — is `surface`
                     if (parent < 0) {
-                        wf_store_pixel(out_rgb, out_rgb8, out_index, surface);
+                        wf_store_pixel(out_rgb, out_rgb8, (size_t)out_index, surface);
                     } else {
                         const V3<T> c = surface * k_parent;  // world.rs:127 / 156
                         T* dst = slot == 0 ? nodes[parent].reflected : nodes[parent].refracted;
@@ -483,23 +525,36 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                 }
             }
         }
-    }
-
-    if (counters) {
-        unsigned int vals[5] = {c_primary, c_shadow, c_reflect, c_refract, c_nodes};
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            unsigned int v = vals[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0 && v) atomicAdd(&counters[k], (unsigned long long)v);
+        // ---- the item's contribution to the work counters ----
+        {
+            const unsigned b_primary = __ballot_sync(0xffffffffu, is_primary), b_nodes = __ballot_sync(0xffffffffu, alive);
+            const unsigned b_reflect = __ballot_sync(0xffffffffu, alive && (flags & FR_REFLECT));
+            const unsigned b_refract = __ballot_sync(0xffffffffu, alive && (flags & FR_REFRACT));
+            if (lane == 0) {
+                my_count[0] += (unsigned)__popc(b_primary);
+                my_count[1] += (unsigned)__popc(b_reflect);
+                my_count[2] += (unsigned)__popc(b_refract);
+                my_count[3] += (unsigned)__popc(b_nodes);
+            }
         }
-        unsigned int px = c_primary;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) px += __shfl_xor_sync(0xffffffffu, px, o);
-        if (lane == 0 && px) atomicAdd(&counters[COUNTER_PIXELS], (unsigned long long)px);
     }
 
+    if (counters && lane == 0) {
+        __syncwarp(1u);
+        const unsigned c_primary = my_count[0], c_reflect = my_count[1], c_refract = my_count[2], c_nodes = my_count[3];
+        if (c_primary) {
+            atomicAdd(&counters[COUNTER_PRIMARY], (unsigned long long)c_primary);
+            atomicAdd(&counters[COUNTER_PIXELS], (unsigned long long)c_primary);
+        }
+        if (c_nodes) {
+            atomicAdd(&counters[COUNTER_HIT_NODES], (unsigned long long)c_nodes);
+            atomicAdd(&counters[COUNTER_SHADOW], (unsigned long long)c_nodes * (unsigned long long)n_lights);  // one per light and node, world.rs:43-53
+        }
+        if (c_reflect) atomicAdd(&counters[COUNTER_REFLECT], (unsigned long long)c_reflect);
+        if (c_refract) atomicAdd(&counters[COUNTER_REFRACT], (unsigned long long)c_refract);
+    }
+
+#undef PK
     // The last CTA to finish closes the level (no separate launch): remember where this level's nodes end, reset
     // the chunk cursor for the next launch, and check that the two ends of the next queue did not meet.
     __syncthreads();

@@ -750,7 +750,8 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
     rt::SceneLayout lay = ctx->layout;
     // staged scene tables (16-byte padded), then one PairScratch per warp for the pair-list trace
     const size_t smem = (SMEM ? ((scene_smem_bytes<T>(ctx) + 15) & ~size_t(15)) : 0) +
-                        ((RT_WF_PAIRS && !BVH) ? (RT_WF_THREADS / 32) * sizeof(rt::PairScratch<T>) : 0);
+                        ((RT_WF_PAIRS && !BVH) ? (RT_WF_THREADS / 32) * sizeof(rt::PairScratch<T>) : 0) +
+                        (size_t)rt::WF_PARK_REALS * RT_WF_THREADS * sizeof(T);
     lay.in_shared = SMEM ? 1u : 0u;
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks_per_sm = 0;

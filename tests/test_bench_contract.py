@@ -9,6 +9,8 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import launches_per_frame  # noqa: E402
 
 BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
              "dtype", "data", "config", "e2e", "cpu_baseline"}
@@ -30,6 +32,17 @@ def test_reference_arm_prints_one_json_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"].startswith("cover.yaml")
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm must not shrink to one core because of it
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+
+
+def test_reference_arm_ignores_omp_num_threads():
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--width", "96",
+                           "--height", "54"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    line = json.loads(proc.stdout.strip())
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
 
 
 def test_reference_arm_other_ranks_exit_quietly():
@@ -44,8 +57,12 @@ def test_b200_arm_line_has_the_contract_keys():
     line = run_bench("--steps", "3", "--warmup", "3", "--width", "320", "--height", "180")
     assert BASE_KEYS | {"gpu_launches", "roofline", "clocks"} <= set(line)
     assert line["n_gpus"] == 1 and line["steps"] == 3 and line["dtype"] == "f64" and line["vs_baseline"] is None
-    assert line["config"]["family"] in ("persistent", "wavefront")
-    assert line["gpu_launches"] == 3 * (1 if line["config"]["family"] == "persistent" else 15)
+    assert line["family"] in ("persistent", "wavefront")
+    assert set(line["config"]) == {"workload", "scene", "width", "height", "precision", "max_depth", "shapes", "lights", "cache"}  # = the reference arm's
+    assert line["gpu_launches"] == 3 * launches_per_frame(line["family"], 6)
+    # pixel identity the driver can read: both legs' frames equal a 1-GPU render, and their RGB8 equals the oracle's
+    assert line["frame"]["frame_matches_n1"] is True and len(line["frame"]["frame_sha256"]) == 64
+    assert line["frame"]["rgb8_pixels_differing_from_oracle"] == 0
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
     assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-12
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] == 320 * 180 * 3 * 8 + 48
