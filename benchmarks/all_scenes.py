@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--precision", default="f64")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--family", default=None, choices=[None, "persistent", "wavefront"], help="force a kernel family (default: the library's measured choice)")
     args = ap.parse_args()
     results = []
     for name in SHIPPED_SCENES:
@@ -36,9 +37,9 @@ def main():
         with Renderer(flat) as r:
             times = []
             for _ in range(args.frames + 1):
-                rgb, rgb8, st = r.render(cam, precision=args.precision)
+                rgb, rgb8, st = r.render(cam, precision=args.precision, family=args.family)
                 times.append(st["kernel_ms"])
-        rec = {"scene": name, "width": w, "height": h, "kernel_ms": min(times[1:]), "rays": st["rays"],
+        rec = {"scene": name, "family": st["family"], "width": w, "height": h, "kernel_ms": min(times[1:]), "rays": st["rays"],
                "mrays_per_s": st["rays"] / (min(times[1:]) * 1e-3) / 1e6, "rays_per_pixel": st["rays"] / st["pixels"]}
         if not args.no_cpu:
             from oracle.oracle import Oracle, max_threads

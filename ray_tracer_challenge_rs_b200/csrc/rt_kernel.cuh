@@ -41,8 +41,8 @@ namespace rt {
 #ifndef RT_TMA_STAGE
 #define RT_TMA_STAGE 1  // scene tables -> shared memory by cp.async.bulk + mbarrier (0: plain loads).  Must precede stage_scene.
 #endif
-#ifndef RT_CULL_PREFETCH
-#define RT_CULL_PREFETCH 0
+#ifndef RT_LEAN_LOOP
+#define RT_LEAN_LOOP 1  // trace_unified: pointer-driven shape loop with a single branch per culled shape
 #endif
 #ifndef RT_CULL
 #define RT_CULL 1  // bounding-sphere pre-test in the intersection loop (exact results either way)
@@ -733,6 +733,50 @@ RT_DEV void trace_bvh(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<
     }
 }
 
+// ptxas prefers recomputing a cheap loop invariant in every iteration to holding it in a register; an empty asm
+// makes the value opaque, so it is computed once.
+RT_DEV void keep_in_register(double& v) { asm volatile("" : "+d"(v)); }
+RT_DEV void keep_in_register(float& v) { asm volatile("" : "+f"(v)); }
+
+// The shape loop's only loop-carried state: where the next cull record is.
+template <typename T, bool SMEM>
+struct CullCursor;
+template <typename T>
+struct CullCursor<T, true> {  // tables in shared memory: shared-window byte addresses
+    uint32_t at, end;
+    template <typename SV>
+    RT_DEV CullCursor(const SV& sv, uint32_t n) {
+        at = (uint32_t)__cvta_generic_to_shared(sv.cull(0));
+        end = at + n * (uint32_t)(CULL_REALS * sizeof(T));
+        asm volatile("" : "+r"(end));  // opaque: a register, not eight uniform instructions per iteration to rebuild it
+    }
+    RT_DEV bool done() const { return at == end; }
+    RT_DEV void next() { at += (uint32_t)(CULL_REALS * sizeof(T)); }
+    RT_DEV void finish() { at = end - (uint32_t)(CULL_REALS * sizeof(T)); }  // the loop's increment then ends it
+    RT_DEV uint32_t position(uint32_t n) const { return n - (end - at) / (uint32_t)(CULL_REALS * sizeof(T)); }
+    RT_DEV void load(double& x, double& y, double& z, double& w) const {
+        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(at));
+        asm("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(z), "=d"(w) : "r"(at));
+    }
+    RT_DEV void load(float& x, float& y, float& z, float& w) const {
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(at));
+    }
+};
+template <typename T>
+struct CullCursor<T, false> {  // tables in global memory
+    const T *at, *end;
+    template <typename SV>
+    RT_DEV CullCursor(const SV& sv, uint32_t n) {
+        at = sv.cull(0);
+        end = at + (size_t)n * CULL_REALS;
+    }
+    RT_DEV bool done() const { return at == end; }
+    RT_DEV void next() { at += CULL_REALS; }
+    RT_DEV void finish() { at = end - CULL_REALS; }
+    RT_DEV uint32_t position(uint32_t n) const { return n - (uint32_t)((end - at) / CULL_REALS); }
+    RT_DEV void load(T& x, T& y, T& z, T& w) const { load_cull(at, x, y, z, w); }
+};
+
 // World::collect_intersections (world.rs:25-35) over the uniform list.  One loop with a warp-uniform switch on
 // the shape type: the pre-test, the object-space transform and the query bookkeeping exist ONCE in the instruction
 // stream instead of once per shape type.  The kernels are bound by instruction supply (GPC instruction cache
@@ -751,22 +795,38 @@ RT_DEV void trace_bvh(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<
 template <typename T, bool FULL, bool SHADOW_EXIT, bool SMEM>
 RT_DEV void trace_unified(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
     const uint32_t n = sv.L.type_begin[NUM_SHAPE_TYPES];
-#if RT_CULL && RT_CULL_PREFETCH
-    // the record of the NEXT shape is loaded one iteration ahead: the pre-test's first operation used to wait for its
-    // own shared-memory load every iteration (ncu: 26 % of the loop's stall samples on that scoreboard)
-    T ncx = T(0), ncy = T(0), ncz = T(0), nr2 = T(0);
-    if (n) load_cull(sv.cull(0), ncx, ncy, ncz, nr2);
-#endif
+#if RT_CULL && RT_LEAN_LOOP
+    // The loop runs on the cull-record pointer alone: a culled shape (88 % of them on the cover frame) costs the
+    // pre-test, one add, one compare and one branch.  Everything else — the shape's position, the addresses of its
+    // geometry and meta records — is derived from the pointer on the rare path; the `asm` keeps the compiler from
+    // turning those addresses back into loop-carried counters (it emitted five adds per iteration).  The pre-test is
+    // evaluated without short-circuits (one data-dependent branch instead of two), and a shadow query that has found
+    // its blocker leaves by moving the pointer to the last record instead of a `break` (no per-iteration
+    // BSSY / BSYNC pair around the body).
+    // shared-memory tables: a 32-bit shared-window address and ld.shared, so that the loop carries two registers
+    // (ptxas otherwise rebuilds the window base from SR_CgaCtaId in every iteration); global tables: a pointer
+    CullCursor<T, SMEM> cur(sv, n);
+    // "the centre is behind the origin" only culls when negative distances are of no interest (everything but the
+    // container walk): comparing against -max instead of 0 switches it off without a mode test in the loop
+    T behind_below = acc.mode == MODE_CONTAINER ? -Real<T>::max() : T(0);
+    keep_in_register(behind_below);
+    for (; !cur.done(); cur.next()) {
+        T cx, cy, cz, r2;
+        cur.load(cx, cy, cz, r2);
+        const T ocx = cx - ray.o.x, ocy = cy - ray.o.y, ocz = cz - ray.o.z;
+        const T bq = fma(ocz, ray.d.z, fma(ocy, ray.d.y, ocx * ray.d.x));
+        const T c2 = fma(ocz, ocz, fma(ocy, ocy, ocx * ocx));
+        const T ex = fma(c2, sv.cull_shrink(), -r2);
+        const bool outside = ex > T(0), behind = bq < behind_below, misses = ex * acc.dir_sq > bq * bq;
+        if (outside & (behind | misses)) continue;
+        uint32_t pos = cur.position(n);
+        asm volatile("" : "+r"(pos));
+#else
     for (uint32_t pos = 0; pos < n; ++pos) {
 #if RT_CULL
         {
-#if RT_CULL_PREFETCH
-            const T cx = ncx, cy = ncy, cz = ncz, r2 = nr2;
-            load_cull(sv.cull(pos + 1u < n ? pos + 1u : pos), ncx, ncy, ncz, nr2);
-#else
             T cx, cy, cz, r2;
             load_cull(sv.cull(pos), cx, cy, cz, r2);
-#endif
             const T ocx = cx - ray.o.x, ocy = cy - ray.o.y, ocz = cz - ray.o.z;
             const T bq = fma(ocz, ray.d.z, fma(ocy, ray.d.y, ocx * ray.d.x));
             const T c2 = fma(ocz, ocz, fma(ocy, ocy, ocx * ocx));
@@ -774,24 +834,29 @@ RT_DEV void trace_unified(const SceneView<T, SMEM>& sv, const Ray<T>& ray, Trace
             if (ex > T(0) && ((acc.mode != MODE_CONTAINER && bq < T(0)) || ex * acc.dir_sq > bq * bq)) continue;
         }
 #endif
+#endif
         const T* g = sv.shape(pos);
         const int4 meta = sv.shape_meta(pos);
         Ray<T> local;  // ray.rs:45-49
         local.o = mat_point(g, ray.o);
         local.d = mat_vector(g, ray.d);
-        T t0 = T(0), t1 = T(0), t2 = T(0), t3 = T(0);
+        T t0, t1, t2, t3;  // set by every local_intersect
         int k = 0;
         switch ((meta.z >> FLAG_TYPE_SHIFT) & 7) {
         case 0: k = local_intersect<T, 0>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
         case 1: k = local_intersect<T, 1>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
         case 2: k = local_intersect<T, 2>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
-        case 3: if (FULL) k = local_intersect<T, 3>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
-        case 4: if (FULL) k = local_intersect<T, 4>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
-        default: if (FULL) k = local_intersect<T, 5>(local, g, meta.z, sv.triangle(pos), t0, t1, t2, t3); break;
+        case 3: if (FULL) k = local_intersect<T, 3>(local, g, meta.z, nullptr, t0, t1, t2, t3); else t0 = t1 = t2 = t3 = T(0); break;
+        case 4: if (FULL) k = local_intersect<T, 4>(local, g, meta.z, nullptr, t0, t1, t2, t3); else t0 = t1 = t2 = t3 = T(0); break;
+        default: if (FULL) k = local_intersect<T, 5>(local, g, meta.z, sv.triangle(pos), t0, t1, t2, t3); else t0 = t1 = t2 = t3 = T(0); break;
         }
         consume<T, 4>(acc, k, t0, t1, t2, t3, (int)pos, meta);
         // World::is_in_shadow (world.rs:106-111) is an `any`: a lane that has found a blocker is done
+#if RT_CULL && RT_LEAN_LOOP
+        if (SHADOW_EXIT && acc.mode == MODE_SHADOW && acc.best_pos >= 0) cur.finish();
+#else
         if (SHADOW_EXIT && acc.mode == MODE_SHADOW && acc.best_pos >= 0) break;
+#endif
     }
 }
 

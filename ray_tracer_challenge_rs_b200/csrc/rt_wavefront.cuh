@@ -79,7 +79,10 @@ struct WfCounts {
 #define RT_WF_THREADS 128
 #endif
 #ifndef RT_WF_MIN_BLOCKS
-#define RT_WF_MIN_BLOCKS 6
+#define RT_WF_MIN_BLOCKS 6  // sphere / plane / cube kernels: 80 registers, no spills worth mentioning
+#endif
+#ifndef RT_WF_MIN_BLOCKS_FULL
+#define RT_WF_MIN_BLOCKS_FULL 4  // kernels that also hold the cylinder / cone / triangle tests spill below ~120 registers (cylinders: 1.07 ms at 6, 0.93 at 4)
 #endif
 
 template <typename T>
@@ -138,7 +141,7 @@ RT_DEV void wf_trace(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<T
 }
 
 template <typename T, bool FULL, bool BVH, bool SMEM>
-__global__ void __launch_bounds__(RT_WF_THREADS, RT_WF_MIN_BLOCKS)
+__global__ void __launch_bounds__(RT_WF_THREADS, FULL ? RT_WF_MIN_BLOCKS_FULL : RT_WF_MIN_BLOCKS)
 wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, SceneLayout layout, CameraParams<T> cam, int level,
                 const WfRay<T>* __restrict__ rays_in, WfRay<T>* __restrict__ rays_out, unsigned cap_rays, WfNode<T>* __restrict__ nodes,
                 unsigned cap_nodes, WfCounts* __restrict__ counts, T* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8,
