@@ -14,6 +14,9 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -468,6 +471,59 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     return RTGPU_OK;
 }
 
+// 64-bit hash of every byte a scene description points to (and its counts): rtgpu_render renders many frames of
+// one scene, and packing + uploading it again each time (seconds for a BVH scene) only makes sense when it changed.
+uint64_t hash_words(uint64_t h, const void* data, size_t bytes) {
+    if (!data) return h * 0x9E3779B97F4A7C15ull + bytes;
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    size_t k = 0;
+    for (; k + 8 <= bytes; k += 8) {
+        uint64_t w;
+        memcpy(&w, p + k, 8);
+        h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29;
+    }
+    uint64_t tail = 0;
+    if (k < bytes) memcpy(&tail, p + k, bytes - k);
+    h = (h ^ tail ^ ((uint64_t)bytes << 56)) * 0xC2B2AE3D27D4EB4Full;
+    return h ^ (h >> 32);
+}
+
+uint64_t scene_input_hash(const rtgpu_scene* s) {
+    if (!s) return 0;
+    uint64_t h = 0x243F6A8885A308D3ull;
+    const uint32_t counts[6] = {s->abi_version, s->n_shapes, s->n_triangles, s->n_materials, s->n_patterns, s->n_lights};
+    h = hash_words(h, counts, sizeof(counts));
+    const size_t S = s->n_shapes, NT = s->n_triangles, M = s->n_materials, Q = s->n_patterns, L = s->n_lights;
+    h = hash_words(h, s->shape_type, S);
+    h = hash_words(h, s->shape_inv, S * 12 * sizeof(double));
+    h = hash_words(h, s->shape_min, S * sizeof(double));
+    h = hash_words(h, s->shape_max, S * sizeof(double));
+    h = hash_words(h, s->shape_closed, S);
+    h = hash_words(h, NT ? s->shape_triangle : nullptr, NT ? S * sizeof(int32_t) : 0);
+    h = hash_words(h, s->shape_material, S * sizeof(uint32_t));
+    h = hash_words(h, s->shape_eq_class, S * sizeof(uint32_t));
+    h = hash_words(h, s->tri_vertex_1, NT * 3 * sizeof(double));
+    h = hash_words(h, s->tri_edge_1, NT * 3 * sizeof(double));
+    h = hash_words(h, s->tri_edge_2, NT * 3 * sizeof(double));
+    h = hash_words(h, s->tri_normal, NT * 3 * sizeof(double));
+    h = hash_words(h, s->mat_color, M * 3 * sizeof(double));
+    h = hash_words(h, s->mat_params, M * RTGPU_MAT_PARAM_COUNT * sizeof(double));
+    h = hash_words(h, s->mat_casts_shadow, M);
+    h = hash_words(h, s->mat_pattern, M * sizeof(int32_t));
+    h = hash_words(h, s->pat_type, Q);
+    h = hash_words(h, s->pat_color_a, Q * 3 * sizeof(double));
+    h = hash_words(h, s->pat_color_b, Q * 3 * sizeof(double));
+    h = hash_words(h, s->pat_inv, Q * 12 * sizeof(double));
+    h = hash_words(h, s->pat_child_a, Q * sizeof(int32_t));
+    h = hash_words(h, s->pat_child_b, Q * sizeof(int32_t));
+    h = hash_words(h, s->light_position, L * 3 * sizeof(double));
+    h = hash_words(h, s->light_intensity, L * 3 * sizeof(double));
+    const char* bvh_min = getenv("RTGPU_BVH_MIN");  // changes what pack_scene builds from the same input
+    h = hash_words(h, bvh_min, bvh_min ? strlen(bvh_min) : 0);
+    return h ? h : 1;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Rows of a launch
 
@@ -481,20 +537,25 @@ int normalise_rows(const rtgpu_rows* rows, uint32_t vsize, RowSel* out) {
     r.shard_count = (rows && rows->shard_count) ? rows->shard_count : 1u;
     r.shard_index = rows ? rows->shard_index : 0u;
     if (r.shard_index >= r.shard_count) return fail(RTGPU_ERR_INVALID_ARGUMENT, "rows.shard_index %u >= shard_count %u", r.shard_index, r.shard_count);
+    // a band taller than the image is the whole image; the period (band_rows * shard_count) must fit 32 bits so that
+    // the kernels' row arithmetic cannot wrap
+    if (vsize && r.band_rows > vsize) r.band_rows = vsize;
+    if ((uint64_t)r.band_rows * r.shard_count > 0xFFFFFFFFull)
+        return fail(RTGPU_ERR_INVALID_ARGUMENT, "rows.band_rows %u x shard_count %u overflows", r.band_rows, r.shard_count);
     *out = r;
     return RTGPU_OK;
 }
 
 uint32_t count_rows(const RowSel& r, uint32_t vsize) {
-    uint32_t n = 0;
-    const uint32_t period = r.band_rows * r.shard_count;
+    const uint64_t period = (uint64_t)r.band_rows * r.shard_count;
+    if (period == 0) return 0;
     // full periods, then the tail
-    const uint32_t full = vsize / period;
-    n = full * r.band_rows;
-    const uint32_t rem = vsize - full * period;
-    const uint32_t lo = r.shard_index * r.band_rows;
-    if (rem > lo) n += std::min(r.band_rows, rem - lo);
-    return n;
+    const uint64_t full = vsize / period;
+    uint64_t n = full * r.band_rows;
+    const uint64_t rem = vsize - full * period;
+    const uint64_t lo = (uint64_t)r.shard_index * r.band_rows;
+    if (rem > lo) n += std::min<uint64_t>(r.band_rows, rem - lo);
+    return (uint32_t)n;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -548,6 +609,15 @@ struct rtgpu_context {
     uint64_t tune_pending_key = 0;
     uint64_t tune_last_key = 0;    // key of the host-buffer render in flight
     int last_family = 0;
+    uint64_t uploaded_input_hash = 0;  // scene_input_hash of what upload_scene last put on the device (0 = unknown)
+    // What the host reads after a frame — work counters, overflow flag and the sizes the frame asked for — lands in
+    // pinned, device-mapped memory, written by the last (tiny) kernel of the frame: one stream sync, no copies.
+    struct HostStatus {
+        unsigned long long counters[rt::NUM_COUNTERS];
+        unsigned overflow, max_rays, n_nodes, valid;
+    };
+    HostStatus* h_status = nullptr;   // host view
+    HostStatus* d_status = nullptr;   // device alias of the same memory
 };
 
 namespace {
@@ -594,6 +664,21 @@ int launch_kernel_impl(rtgpu_context* ctx, const T* d_reals, const rt::CameraPar
 
 __global__ void wf_commit_counters_kernel(const unsigned long long* priv, unsigned long long* user) {
     if (threadIdx.x < rt::NUM_COUNTERS && priv[threadIdx.x]) atomicAdd(&user[threadIdx.x], priv[threadIdx.x]);
+}
+
+// Last kernel of a host-buffer frame: everything the host wants to know, written into mapped pinned memory.
+__global__ void publish_status_kernel(const unsigned long long* counters, const rt::WfCounts* wf, rtgpu_context::HostStatus* out) {
+    if (threadIdx.x < rt::NUM_COUNTERS) out->counters[threadIdx.x] = counters ? counters[threadIdx.x] : 0ull;
+    if (threadIdx.x == 0) {
+        unsigned max_rays = 0;
+        if (wf)
+            for (int d = 0; d < 18; ++d) max_rays = max(max_rays, wf->n_rays[d] + wf->n_back[d]);
+        out->overflow = wf ? wf->overflow : 0u;
+        out->max_rays = max_rays;
+        out->n_nodes = wf ? wf->n_nodes : 0u;
+        __threadfence_system();
+        out->valid = 1u;
+    }
 }
 
 enum { FAMILY_PERSISTENT = 0, FAMILY_WAVEFRONT = 1, FAMILY_AUTO = 2 };
@@ -818,18 +903,22 @@ int launch_wavefront(rtgpu_context* ctx, const T* d_reals, const rt::CameraParam
 
 // After a wavefront launch has completed on `stream`: did a queue or the node array overflow?
 // Returns 1 (and enlarges the buffers) when the frame has to be rendered again, 0 when it is complete.
+// published: the frame ended with publish_status_kernel and the stream has been synchronised since — the answer is
+// already in mapped host memory; otherwise it is published and waited for here.
 template <typename T>
-int wavefront_check(rtgpu_context* ctx, uint64_t pixels, cudaStream_t stream) {
+int wavefront_check(rtgpu_context* ctx, uint64_t pixels, cudaStream_t stream, bool published = false) {
     if (!ctx->wf_used) return 0;
     ctx->wf_used = false;
-    rt::WfCounts h;
-    CUDA_TRY(cudaMemcpyAsync(&h, ctx->d_wf_counts, sizeof(h), cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (!published || !ctx->h_status->valid) {
+        ctx->h_status->valid = 0u;
+        publish_status_kernel<<<1, 32, 0, stream>>>(nullptr, ctx->d_wf_counts, ctx->d_status);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    const rtgpu_context::HostStatus h = *ctx->h_status;
     if (!h.overflow) return 0;
     // what the frame actually asked for, with headroom
-    unsigned max_rays = 0;
-    for (int d = 0; d < 18; ++d) max_rays = std::max(max_rays, h.n_rays[d] + h.n_back[d]);
-    const double g_rays = (double)max_rays / (3.0 * (double)pixels), g_nodes = (double)h.n_nodes / (5.0 * (double)pixels);
+    const double g_rays = (double)h.max_rays / (3.0 * (double)pixels), g_nodes = (double)h.n_nodes / (5.0 * (double)pixels);
     const double growth = std::max(1.25 * std::max(g_rays, g_nodes), 2.0 * (double)ctx->wf_cap_rays / (3.0 * (double)pixels));
     int st = wavefront_reserve<T>(ctx, pixels, growth);
     if (st != RTGPU_OK) return st;
@@ -1007,6 +1096,9 @@ int context_init(rtgpu_context* ctx, int device) {
     CUDA_TRY(cudaEventCreate(&ctx->ev1));
     CUDA_TRY(cudaMalloc(&ctx->d_work, sizeof(unsigned int)));
     CUDA_TRY(cudaMalloc(&ctx->d_counters, rt::NUM_COUNTERS * sizeof(unsigned long long)));
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_status), sizeof(rtgpu_context::HostStatus), cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(ctx->h_status, 0, sizeof(rtgpu_context::HostStatus));
+    CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->d_status), ctx->h_status, 0));
     return RTGPU_OK;
 }
 
@@ -1018,6 +1110,7 @@ void context_release(rtgpu_context* ctx) {
     if (ctx->d_ints) cudaFree(ctx->d_ints);
     if (ctx->d_work) cudaFree(ctx->d_work);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->d_out) cudaFree(ctx->d_out);
     if (ctx->d_out8) cudaFree(ctx->d_out8);
     for (int k = 0; k < 2; ++k)
@@ -1066,6 +1159,14 @@ void* mapped_device_pointer(const void* host) {
     return attr.devicePointer;
 }
 
+// The frame's kernels are all enqueued: publish what the host will want to read once the stream has drained.
+int publish_status(rtgpu_context* ctx) {
+    ctx->h_status->valid = 0u;
+    publish_status_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_counters, ctx->wf_used ? ctx->d_wf_counts : nullptr, ctx->d_status);
+    CUDA_TRY(cudaGetLastError());
+    return RTGPU_OK;
+}
+
 // Issue (do not wait for) everything one device does for a host-buffer render: kernel + D2H of its
 // row bands into the full-frame host buffers.
 int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rtgpu_opts* opts, const rtgpu_rows* rows,
@@ -1081,6 +1182,16 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
     const size_t row_rgb = (size_t)camera->hsize * 3 * elem;
     const size_t row_rgb8 = (size_t)camera->hsize * 3;
     CUDA_TRY(cudaSetDevice(ctx->device));
+    if (n_rows == 0 || camera->hsize == 0) {
+        // a shard without rows (more shards than bands): nothing to render or copy, but the caller still waits on
+        // this context's events and reads its (zero) counters
+        ctx->wf_used = false;
+        ctx->zero_copy = false;
+        CUDA_TRY(cudaMemsetAsync(ctx->d_counters, 0, rt::NUM_COUNTERS * sizeof(unsigned long long), ctx->stream));
+        CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+        CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+        return publish_status(ctx);
+    }
     // Zero-copy: when the caller's buffers are pinned, device-mapped host memory the persistent kernel writes each
     // finished pixel straight into the caller's Canvas (full-frame indexing); the PCIe traffic then
     // overlaps the render instead of following it.  Pageable buffers take the staging path below, and so does
@@ -1122,6 +1233,7 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
                                 ctx->stream, nullptr, family, /*full_frame_out=*/true, /*wavefront_blocking=*/false);
         if (st != RTGPU_OK) return st;
         CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+        if ((st = publish_status(ctx)) != RTGPU_OK) return st;
         if (trial) tune_end(ctx, ctx->stream, key, family);
         return RTGPU_OK;
     }
@@ -1140,7 +1252,9 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
             CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_chunk, cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
         }
-        constexpr uint32_t BAND = 16, CHUNKS = 2;
+        constexpr uint32_t BAND = 16;
+        uint32_t CHUNKS = 2;
+        if (chunks_env && chunks_env[0] >= '2' && chunks_env[0] <= '8') CHUNKS = (uint32_t)(chunks_env[0] - '0');
         size_t rows_before = 0;
         for (uint32_t c = 0; c < CHUNKS; ++c) {
             rtgpu_rows sub;
@@ -1164,6 +1278,7 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
                 cs = ctx->copy_stream;
             } else {
                 CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+                if ((st = publish_status(ctx)) != RTGPU_OK) return st;
             }
             // compact band b of this chunk -> image rows of band (b * CHUNKS + c): one strided copy + the partial last band
             const uint32_t full_bands = rows_c / BAND, tail_rows = rows_c % BAND;
@@ -1195,6 +1310,7 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
                             reinterpret_cast<uint64_t*>(ctx->d_counters), ctx->stream, nullptr, family, false, /*wavefront_blocking=*/false);
     if (st != RTGPU_OK) return st;
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+    if ((st = publish_status(ctx)) != RTGPU_OK) return st;
     // compact band b (rows [b*band_rows, ...)) of this shard -> image rows of band (b*shard_count + shard_index)
     for (uint32_t k = 0; k < n_rows; k += sel.band_rows) {
         const uint32_t rows_here = std::min(sel.band_rows, n_rows - k);
@@ -1221,7 +1337,7 @@ int finish_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rtg
         if (st != RTGPU_OK) return st;
         const uint64_t pixels = (uint64_t)camera->hsize * count_rows(sel, camera->vsize);
         const bool f64 = !opts || opts->precision == RTGPU_PRECISION_F64;
-        st = f64 ? wavefront_check<double>(ctx, pixels, ctx->stream) : wavefront_check<float>(ctx, pixels, ctx->stream);
+        st = f64 ? wavefront_check<double>(ctx, pixels, ctx->stream, true) : wavefront_check<float>(ctx, pixels, ctx->stream, true);
         if (st == RTGPU_ERR_OUT_OF_MEMORY && requested_family(opts) == FAMILY_AUTO) {
             // the frame needs larger queues than the device can give: the persistent kernel needs none
             tune_rule_out_wavefront(ctx, ctx->tune_last_key);
@@ -1238,8 +1354,8 @@ int finish_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rtg
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
     if (stats) {
-        unsigned long long c[rt::NUM_COUNTERS];
-        CUDA_TRY(cudaMemcpy(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+        if (!ctx->h_status->valid) return fail(RTGPU_ERR_CUDA, "the frame's status block was not published");
+        const unsigned long long* c = ctx->h_status->counters;
         stats->rays_primary += c[rt::COUNTER_PRIMARY];
         stats->rays_shadow += c[rt::COUNTER_SHADOW];
         stats->rays_reflect += c[rt::COUNTER_REFLECT];
@@ -1332,6 +1448,78 @@ __global__ void selftest_arith_kernel(const double* a, const double* b, size_t n
     atomicAdd(&out[1], sqrt_bad);
     atomicAdd(&out[2], div_fb);
     atomicAdd(&out[3], sqrt_fb);
+}
+
+// Resident helper threads for the multi-device one-shot call: job g runs on helper g - 1 (job 0 on the caller's
+// thread), so a frame costs a wake-up per device instead of a thread creation.
+class WorkerPool {
+public:
+    template <typename F>
+    void run(int n_jobs, F&& fn) {
+        if (n_jobs <= 1) {
+            fn(0);
+            return;
+        }
+        std::function<void(int)> f = fn;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            while ((int)threads_.size() < n_jobs - 1) {
+                const int index = (int)threads_.size();
+                slots_.emplace_back(new Slot());
+                threads_.emplace_back([this, index] { loop(index); });
+            }
+            job_ = &f;
+            pending_ = n_jobs - 1;
+            for (int k = 0; k < n_jobs - 1; ++k) slots_[k]->go = true;
+        }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [this] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+    ~WorkerPool() {
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+
+private:
+    struct Slot {
+        bool go = false;
+    };
+    void loop(int index) {
+        for (;;) {
+            std::function<void(int)>* job = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || slots_[index]->go; });
+                if (stop_) return;
+                slots_[index]->go = false;
+                job = job_;
+            }
+            (*job)(index + 1);
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                if (--pending_ == 0) done_cv_.notify_all();
+            }
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<std::thread> threads_;
+    std::vector<std::unique_ptr<Slot>> slots_;
+    std::function<void(int)>* job_ = nullptr;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
+WorkerPool& worker_pool() {
+    static WorkerPool* pool = new WorkerPool();  // leaked on purpose: no thread joins during static destruction
+    return *pool;
 }
 
 }  // namespace
@@ -1439,21 +1627,28 @@ int rtgpu_render(const rtgpu_scene* scene, const rtgpu_camera* camera, const rtg
     if (!out_rgb && !out_rgb8) return fail(RTGPU_ERR_INVALID_ARGUMENT, "both output pointers are NULL");
     const double t0 = wall_ms();
     if (stats) memset(stats, 0, sizeof(*stats));
-    PackedScene packed;
-    int st = pack_scene(scene, &packed);
-    if (st != RTGPU_OK) return st;
-    const int available = rtgpu_device_count();
-    if (available <= 0) return fail(RTGPU_ERR_NO_DEVICE, "no CUDA device available (gpu mode has no CPU fallback)");
-    int n_gpus = (opts && opts->n_gpus > 0) ? opts->n_gpus : 1;
-    if (n_gpus > available) return fail(RTGPU_ERR_INVALID_ARGUMENT, "opts.n_gpus %d > %d visible devices", n_gpus, available);
-    uint32_t band_rows = (opts && opts->band_rows) ? opts->band_rows : 16u;
-    band_rows = (band_rows + 3u) & ~3u;  // whole 8x4 tiles per band
-
+    if (!scene) return fail(RTGPU_ERR_INVALID_ARGUMENT, "scene is NULL");
+    int st = RTGPU_OK;
     // One resident scene per device, kept for the lifetime of the process so that repeated frames
-    // pay for the upload but not for cudaMalloc / stream creation.
+    // pay for neither cudaMalloc / stream creation nor — when the scene description is byte-for-byte the one the
+    // device already holds — for validation, packing (BVH build) and upload.
     static std::mutex mu;
     static std::vector<rtgpu_context*> cache;
     std::lock_guard<std::mutex> lock(mu);
+    int n_gpus = (opts && opts->n_gpus > 0) ? opts->n_gpus : 1;
+    const uint64_t input_hash = scene_input_hash(scene);
+    bool need_pack = (int)cache.size() < n_gpus;
+    for (int g = 0; g < n_gpus && !need_pack; ++g) need_pack = !cache[g] || cache[g]->uploaded_input_hash != input_hash;
+    PackedScene packed;
+    if (need_pack) {
+        st = pack_scene(scene, &packed);  // validates: a malformed scene is reported before anything touches a device
+        if (st != RTGPU_OK) return st;
+    }
+    const int available = rtgpu_device_count();
+    if (available <= 0) return fail(RTGPU_ERR_NO_DEVICE, "no CUDA device available (gpu mode has no CPU fallback)");
+    if (n_gpus > available) return fail(RTGPU_ERR_INVALID_ARGUMENT, "opts.n_gpus %d > %d visible devices", n_gpus, available);
+    uint32_t band_rows = (opts && opts->band_rows) ? opts->band_rows : 16u;
+    band_rows = (band_rows + 3u) & ~3u;  // whole 8x4 tiles per band
     if ((int)cache.size() < n_gpus) cache.resize(n_gpus, nullptr);
     for (int g = 0; g < n_gpus; ++g) {
         if (!cache[g]) {
@@ -1469,8 +1664,8 @@ int rtgpu_render(const rtgpu_scene* scene, const rtgpu_camera* camera, const rtg
         }
     }
     // row bands: device g renders bands g, g+G, g+2G, ... (interleaved: per-row cost varies a lot).
-    // One host thread per device (the caller's for device 0): upload, launches, copies and the final wait of the
-    // devices proceed side by side instead of queueing behind one another on a single submitting thread.
+    // One host thread per device (the caller's for device 0, resident workers for the others): upload, launches,
+    // copies and the final wait of the devices proceed side by side instead of queueing behind one another.
     struct DeviceJob {
         int status = RTGPU_OK;
         std::string error;
@@ -1484,18 +1679,17 @@ int rtgpu_render(const rtgpu_scene* scene, const rtgpu_camera* camera, const rtg
         rows.shard_index = (uint32_t)g;
         rows.shard_count = (uint32_t)n_gpus;
         int rc = cudaSetDevice(g) == cudaSuccess ? RTGPU_OK : fail(RTGPU_ERR_CUDA, "cudaSetDevice(%d) failed", g);
-        if (rc == RTGPU_OK) rc = upload_scene(cache[g], packed);
+        if (rc == RTGPU_OK && cache[g]->uploaded_input_hash != input_hash) {
+            cache[g]->uploaded_input_hash = 0;
+            rc = upload_scene(cache[g], packed);
+            if (rc == RTGPU_OK) cache[g]->uploaded_input_hash = input_hash;
+        }
         if (rc == RTGPU_OK) rc = enqueue_host_render(cache[g], camera, opts, &rows, out_rgb, out_rgb8);
         if (rc == RTGPU_OK) rc = finish_host_render(cache[g], camera, opts, &rows, out_rgb, out_rgb8, stats ? &job.stats : nullptr);
         job.status = rc;
         if (rc != RTGPU_OK) job.error = g_last_error;
     };
-    {
-        std::vector<std::thread> helpers;
-        for (int g = 1; g < n_gpus; ++g) helpers.emplace_back(work, g);
-        work(0);
-        for (auto& t : helpers) t.join();
-    }
+    worker_pool().run(n_gpus, work);
     for (int g = 0; g < n_gpus; ++g) {
         if (jobs[g].status != RTGPU_OK) {
             g_last_error = jobs[g].error;

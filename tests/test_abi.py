@@ -53,6 +53,16 @@ def test_rows_helpers_partition_the_frame(lib, vsize, band, count):
     assert sorted(seen) == list(range(vsize))
 
 
+def test_rows_arithmetic_cannot_wrap(lib):
+    """band_rows * shard_count is computed in 64 bits: a product that overflows 32 bits is rejected (count 0), a band
+    taller than the image is the whole image."""
+    assert lib.rtgpu_rows_count(C.byref(abi.RtgpuRows(65536, 0, 65536)), 1080) == 1080  # band clamped to the image: one band, shard 0
+    assert lib.rtgpu_rows_count(C.byref(abi.RtgpuRows(65536, 1, 65536)), 1080) == 0
+    assert lib.rtgpu_rows_count(C.byref(abi.RtgpuRows(4096, 0, 0x00200000)), 0xFFFFFFFF) == 0  # 2^12 * 2^21 wraps: rejected
+    assert lib.rtgpu_rows_count(C.byref(abi.RtgpuRows(0xFFFFFFFF, 0, 1)), 100) == 100
+    assert lib.rtgpu_rows_count(C.byref(abi.RtgpuRows(16, 3, 2)), 100) == 0  # shard_index >= shard_count
+
+
 def test_no_device_is_a_loud_error(lib):
     if lib.rtgpu_device_count() > 0:
         pytest.skip("a GPU is visible")

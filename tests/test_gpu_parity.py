@@ -67,6 +67,57 @@ def test_special_world(name):
     compare_with_oracle(world.flatten(), camera, label=name)
 
 
+def test_empty_shard_renders_nothing():
+    """More shards than row bands: the shards without rows succeed, report zero work and leave the frame untouched
+    (a fresh context has no staging buffers yet)."""
+    flat, camera = load_scene_fixture("three_sphere_scene")
+    cam = camera.resized(64, 40)  # 16-row bands: 3 bands, shards 3..7 of 8 are empty
+    for family in ("persistent", "wavefront"):
+        with Renderer(flat) as r:
+            assert r.rows_count(cam, (16, 5, 8)) == 0
+            rgb = np.full((64 * 40, 3), 7.0)
+            rgb8 = np.full((64 * 40, 3), 9, np.uint8)
+            _, _, st = r.render(cam, rows=(16, 5, 8), out_rgb=rgb, out_rgb8=rgb8, family=family)
+            assert st["rays"] == 0 and st["pixels"] == 0
+            assert (rgb == 7.0).all() and (rgb8 == 9).all()
+            whole, whole8, _ = r.render(cam, family=family)
+            parts, parts8 = np.zeros_like(whole), np.zeros_like(whole8)
+            for index in range(8):
+                r.render(cam, rows=(16, index, 8), out_rgb=parts, out_rgb8=parts8, family=family)
+            assert np.array_equal(parts, whole) and np.array_equal(parts8, whole8)
+
+
+def test_output_buffers_are_validated():
+    flat, camera = load_scene_fixture("three_sphere_scene")
+    cam = camera.resized(32, 16)
+    with Renderer(flat) as r:
+        with pytest.raises(ValueError):
+            r.render(cam, out_rgb=np.zeros((32 * 16, 3), np.float32))  # f64 mode writes 8-byte elements
+        with pytest.raises(ValueError):
+            r.render(cam, out_rgb=np.zeros((32 * 8, 3)))  # half a frame
+        with pytest.raises(ValueError):
+            r.render(cam, out_rgb=np.zeros((32 * 16, 6))[:, ::2])  # not contiguous
+        with pytest.raises(ValueError):
+            r.render(cam, precision="f32", out_rgb=np.zeros((32 * 16, 3)))  # f32 mode writes 4-byte elements
+        with pytest.raises(ValueError):
+            r.render(cam, out_rgb8=np.zeros((32 * 16, 3), np.int8))
+
+
+def test_one_shot_call_reuses_the_resident_scene():
+    """rtgpu_render keeps one context per device: a second frame of a byte-identical scene description skips packing
+    and upload, a changed description is uploaded again — the pixels say which scene was rendered."""
+    flat_a, camera = load_scene_fixture("three_sphere_scene")
+    flat_b, _ = load_scene_fixture("metal")
+    cam = camera.resized(96, 64)
+    a1 = render_gpu(cam, flat_a).to_rgb8()
+    a2 = render_gpu(cam, flat_a).to_rgb8()
+    b1 = render_gpu(cam, flat_b).to_rgb8()
+    a3 = render_gpu(cam, flat_a).to_rgb8()
+    assert np.array_equal(a1, a2) and np.array_equal(a1, a3) and not np.array_equal(a1, b1)
+    assert np.array_equal(b1, Oracle(flat_b).render(cam)[1].reshape(b1.shape))
+    assert np.array_equal(a3, Oracle(flat_a).render(cam)[1].reshape(a3.shape))
+
+
 @pytest.mark.parametrize("max_depth", [0, 1, 3, 5, 7, 9])
 def test_recursion_depths(max_depth):
     flat, camera = load_scene_fixture("refraction")

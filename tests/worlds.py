@@ -96,7 +96,23 @@ def default_world(w=11, h=11):
     return World.default(), _cam(w, h, math.pi / 2, (0, 0, -5), (0, 0, 0))
 
 
+def light_on_surface_world(w=128, h=96):
+    """Lights that lie exactly ON shadow-casting surfaces (a plane, a cube face): for many pixels the shadow ray
+    meets that surface at exactly the light's distance.  The reference's test is strict, `0 <= t < distance`
+    (intersection.rs:77-79 via world.rs:98-112): such points are lit."""
+    wall = Plane(Material(color=(0.8, 0.8, 0.9), specular=0.0), P.mat_mul(P.translation(0, 0, 4), P.rotation_x(math.pi / 2)))
+    floor = Plane(Material(pattern=CheckerPattern((0.9, 0.9, 0.9), (0.3, 0.3, 0.3)), specular=0.0))
+    box = Cube(Material(color=(0.9, 0.4, 0.2), reflectiveness=0.2), P.mat_mul(P.translation(1.5, 1.0, 1.0), P.scaling(1, 1, 1)))
+    ball = Sphere(Material(color=(0.2, 0.6, 0.9)), P.translation(-1.5, 1.0, 0.5))
+    lights = [Light((0.0, 2.0, 4.0), (0.7, 0.7, 0.7)),    # on the wall z = 4
+              Light((0.5, 1.0, 2.0), (0.4, 0.4, 0.4)),    # on the cube face x = 0.5 ... and on its edge region y in [0, 2]
+              Light((-3.0, 0.0, -1.0), (0.3, 0.3, 0.3))]  # on the floor y = 0
+    world = World(lights, [wall, floor, box, ball])
+    return world, _cam(w, h, 1.1, (0.3, 2.5, -6.0), (0.0, 1.0, 1.0))
+
+
 SPECIAL_WORLDS = {
+    "light_on_surface": light_on_surface_world,
     "all_shapes": all_shapes_world,
     "duplicate_glass": duplicate_glass_world,
     "mirror_box": mirror_box_world,
