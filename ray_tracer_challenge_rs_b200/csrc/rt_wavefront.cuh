@@ -87,11 +87,7 @@ struct WfCounts {
 
 template <typename T>
 RT_DEV void wf_store_pixel(T* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8, size_t out_index, V3<T> colour) {
-    if (out_rgb) {
-        out_rgb[out_index * 3 + 0] = colour.x;
-        out_rgb[out_index * 3 + 1] = colour.y;
-        out_rgb[out_index * 3 + 2] = colour.z;
-    }
+    if (out_rgb) store_rgb(out_rgb + out_index * 3, colour);
     if (out_rgb8) {  // Canvas::to_png_file, canvas.rs:117-123
         const T ch[3] = {colour.x, colour.y, colour.z};
 #pragma unroll

@@ -153,6 +153,49 @@ def test_cover_1080p_against_oracle():
     print(f"cover@1080p: {n_differ} pixels differ in f64 (max rel {worst:.2e})")
 
 
+# ---- BASELINE.json configs[2..4] at the sizes BASELINE.json states -------------------------------------------------
+@pytest.mark.parametrize("name,family", [("reflect_refract", "wavefront"), ("refraction", "wavefront"), ("refraction", "persistent")])
+def test_baseline_config2_4k_depth5(name, family):
+    """configs[2]: reflect_refract.yaml + refraction.yaml at 3840x2160, max recursion depth 5, whole frame vs the oracle."""
+    flat, camera = load_scene_fixture(name)
+    n_differ, worst = compare_with_oracle(flat, camera.resized(3840, 2160), max_depth=5, label=f"{name}@4k/5", family=family)
+    print(f"{name}@3840x2160 depth 5 ({family}): {n_differ} pixels differ in f64 (max rel {worst:.2e})")
+
+
+@pytest.mark.parametrize("name", ["cylinders", "table", "shadow_puppets"])
+def test_baseline_config3_1080p(name):
+    """configs[3]: cube / cylinder / cone intersections and multi-light shadow rays at 1920x1080, whole frame vs the oracle."""
+    flat, camera = load_scene_fixture(name)
+    for family in ("persistent", "wavefront"):
+        n_differ, worst = compare_with_oracle(flat, camera.resized(1920, 1080), label=f"{name}@1080p", family=family)
+        print(f"{name}@1920x1080 ({family}): {n_differ} pixels differ in f64 (max rel {worst:.2e})")
+
+
+def test_baseline_config4_synthetic_100k_at_8k():
+    """configs[4]: 10^5 spheres + triangles with random materials and patterns at 7680x4320 (the BVH path), 4096
+    sampled pixels against the brute-force oracle (a whole 8K frame of 10^5 shapes is a day of CPU time), plus the
+    frame's sharding property: 8 interleaved row-band shards reproduce the unsharded frame byte for byte."""
+    from ray_tracer_challenge_rs_b200.synthetic import synthetic_camera, synthetic_scene
+
+    flat = synthetic_scene(100000)
+    cam = synthetic_camera(7680, 4320)
+    with Renderer(flat) as r:
+        rgb, rgb8, st = r.render(cam)
+        px = np.random.default_rng(4).integers(0, 7680 * 4320, 4096).astype(np.uint64)
+        ref, ref8, ost = Oracle(flat).render_pixels(cam, px)
+        idx = px.astype(np.int64)
+        assert np.array_equal(rgb8[idx], ref8), "RGB8 of sampled pixels differs from the oracle"
+        worst = float((np.abs(rgb[idx] - ref) / np.maximum(np.abs(ref), 1.0)).max())
+        assert worst <= F64_RTOL, worst
+        assert st["pixels"] == 7680 * 4320
+        digest = hashlib.sha256(rgb8.tobytes()).hexdigest()
+        parts8 = np.zeros_like(rgb8)
+        for index in range(8):
+            r.render(cam, rows=(16, index, 8), out_rgb8=parts8, want_rgb=False)
+        assert hashlib.sha256(parts8.tobytes()).hexdigest() == digest
+    print(f"synthetic 1e5 @ 8K: {st['rays']} rays, kernel {st['kernel_ms']:.1f} ms, sample max rel {worst:.2e}")
+
+
 @pytest.mark.parametrize("band,count", [(16, 2), (16, 4), (4, 8), (5, 3)])
 def test_row_band_shards_equal_whole_frame(band, count):
     """What N GPUs would each render (rtgpu_rows) assembles to exactly the unsharded frame."""
