@@ -263,6 +263,40 @@ int rtgpu_measure_fma_peak(int device, uint32_t precision, double *out_tflops, d
 int rtgpu_selftest_arith(int device, const double *a, const double *b, size_t n, uint64_t *out_div_mismatches,
                          uint64_t *out_sqrt_mismatches, uint64_t *out_div_fallbacks, uint64_t *out_sqrt_fallbacks);
 
+/* -- known-answer probes -------------------------------------------------------------------- */
+/* ONE device thread evaluates the device functions the render kernels are built from on the caller's inputs, so
+ * that the reference's own unit tests can be replayed on the GPU value by value (tests/test_gpu_kat.py).  Test
+ * infrastructure: not on the render path.  `in` / `out` are host arrays of doubles; integers (shape = index into
+ * world.shapes, material, pattern, light, flags) travel as doubles.  Scene queries (IN_SHADOW, PREPARE) need a
+ * scene below the BVH threshold.  f64 only. */
+typedef enum rtgpu_probe_kind {
+    RTGPU_PROBE_RAY_FOR_PIXEL = 0, /* Camera::ray_for_pixel, camera.rs:52-68.  in: px, py.  out: origin[3], direction[3]       */
+    RTGPU_PROBE_INTERSECT = 1,     /* Ray::intersect, ray.rs:35-49 + shapes/*.rs local_intersect.  in: shape, origin[3],
+                                      direction[3].  out: n, t[4] (push order)                                                 */
+    RTGPU_PROBE_LOCAL_NORMAL = 2,  /* local_normal_at of the shape's type.  in: shape, object-space point[3].  out: normal[3]   */
+    RTGPU_PROBE_NORMAL = 3,        /* Shape::normal_at, shapes/shape.rs:22-27.  in: shape, world point[3].  out: normal[3]      */
+    RTGPU_PROBE_PATTERN = 4,       /* Pattern::color_at_shape, patterns/pattern.rs:10-14.  in: pattern, shape, point[3].
+                                      out: colour[3]                                                                           */
+    RTGPU_PROBE_LIGHTING = 5,      /* Material::lighting, composites/material.rs:53-114.  in: material, shape, light
+                                      position[3], light intensity[3], point[3], eye[3], normal[3], in_shadow.  out: colour[3] */
+    RTGPU_PROBE_IN_SHADOW = 6,     /* World::is_in_shadow, composites/world.rs:98-112.  in: light, point[3].  out: 0 / 1        */
+    RTGPU_PROBE_PREPARE = 7,       /* Intersections::hit + Intersection::prepare_computations, composites/intersection.rs:21-75,
+                                      + ComputedHit::schlicks_approximation, computed_hit.rs:50-68.  in: origin[3],
+                                      direction[3], k (-1 = the hit), n, then n x (t, shape) = the sorted list.  out: found,
+                                      distance, shape, inside, point[3], over[3], under[3], eye[3], normal[3], reflect[3],
+                                      n1, n2, schlick  (25 values)                                                            */
+    RTGPU_PROBE_QUANTISE = 8,      /* Canvas 8-bit quantisation, composites/canvas.rs:117-123.  in: v.  out: byte              */
+    RTGPU_PROBE_COLLECT = 9        /* World::collect_intersections before its sort, world.rs:25-33.  in: origin[3],
+                                      direction[3].  out: count, then (t, shape) pairs in push order                           */
+} rtgpu_probe_kind;
+int rtgpu_debug_probe(rtgpu_context *context, const rtgpu_camera *camera, uint32_t kind, const double *in, size_t n_in,
+                      double *out, size_t n_out);
+/* World::color_at (world.rs:89-95) of an arbitrary ray — origin, direction as given, not normalised — with
+ * opts->max_depth remaining iterations, through the unmodified render kernels of the family opts->flags names
+ * (default PERSISTENT): a 1 x 1 frame whose only ray is the caller's. */
+int rtgpu_debug_color_at(rtgpu_context *context, const double origin[3], const double direction[3], const rtgpu_opts *opts,
+                         double out_rgb[3]);
+
 #ifdef __cplusplus
 }
 #endif

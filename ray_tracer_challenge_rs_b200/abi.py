@@ -138,7 +138,13 @@ EXPORTED_SYMBOLS = (
     "rtgpu_host_free",
     "rtgpu_measure_fma_peak",
     "rtgpu_selftest_arith",
+    "rtgpu_debug_probe",
+    "rtgpu_debug_color_at",
 )
+
+# rtgpu_probe_kind
+(PROBE_RAY_FOR_PIXEL, PROBE_INTERSECT, PROBE_LOCAL_NORMAL, PROBE_NORMAL, PROBE_PATTERN, PROBE_LIGHTING, PROBE_IN_SHADOW,
+ PROBE_PREPARE, PROBE_QUANTISE, PROBE_COLLECT) = range(10)
 
 PACKAGE_DIR = os.path.dirname(os.path.abspath(__file__))
 LIBRARY_PATH = os.path.join(PACKAGE_DIR, "librtgpu.so")
@@ -218,6 +224,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.rtgpu_host_free.argtypes = [C.c_void_p]
     lib.rtgpu_selftest_arith.restype = C.c_int
     lib.rtgpu_selftest_arith.argtypes = [C.c_int, _pd, _pd, C.c_size_t, _pu64, _pu64, _pu64, _pu64]
+    lib.rtgpu_debug_probe.restype = C.c_int
+    lib.rtgpu_debug_probe.argtypes = [C.c_void_p, C.POINTER(RtgpuCamera), C.c_uint32, _pd, C.c_size_t, _pd, C.c_size_t]
+    lib.rtgpu_debug_color_at.restype = C.c_int
+    lib.rtgpu_debug_color_at.argtypes = [C.c_void_p, _pd, _pd, C.POINTER(RtgpuOpts), _pd]
     if lib.rtgpu_abi_version() != ABI_VERSION:
         raise RuntimeError(f"{p}: ABI version {lib.rtgpu_abi_version()} != {ABI_VERSION}")
     if path is None:

@@ -1070,6 +1070,98 @@ RT_COLD V3<T> pattern_color_at(const SceneView<T, SMEM>& sv, int pattern, V3<T> 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The pieces of a node both kernel families (and the known-answer probes of rt_probe.cuh) are built from.
+
+// Camera::ray_for_pixel, camera.rs:52-68 (x, y: image column and row)
+template <typename T>
+RT_DEV Ray<T> camera_ray(const CameraParams<T>& cam, uint32_t x, uint32_t y) {
+    T offset_x = (T(x) + T(0.5)) * cam.pixel_size;
+    T offset_y = (T(y) + T(0.5)) * cam.pixel_size;
+    T world_x = cam.half_width - offset_x;
+    T world_y = cam.half_height - offset_y;
+    V3<T> pixel = mat_point(cam.inv, mk<T>(world_x, world_y, T(-1)));
+    V3<T> origin = ld3(cam.origin);
+    Ray<T> ray;
+    ray.o = origin;
+    ray.d = normalized(pixel - origin);
+    return ray;
+}
+
+// Shape::normal_at, shape.rs:22-27: world point -> object space -> local normal -> world space, normalised
+template <typename T, bool SMEM>
+RT_DEV V3<T> world_normal_at(const SceneView<T, SMEM>& sv, uint32_t pos, int type, const T* g, V3<T> point) {
+    V3<T> local_point = mat_point(g, point);
+    V3<T> local_normal = local_normal_at(sv, pos, type, g, local_point);
+    return normalized(mat_transposed_vector(g, local_normal));
+}
+
+// World::refracted_color's direction (world.rs:136-150): false on total internal reflection, else the refracted
+// direction is normal * a - eye * n_ratio
+template <typename T>
+RT_DEV bool refraction_coefficients(T n1, T n2, T cos_i, T& a, T& n_ratio) {
+    n_ratio = n1 / n2;
+    T sin2_t = sq(n_ratio) * (T(1) - sq(cos_i));
+    if (sin2_t > T(1)) return false;
+    T cos_t = sqrt(T(1) - sin2_t);
+    a = fma(n_ratio, cos_i, -cos_t);
+    return true;
+}
+
+// ComputedHit::schlicks_approximation, computed_hit.rs:50-68
+template <typename T>
+RT_DEV T schlick_reflectance(T n1, T n2, T cos_i) {
+    T c = cos_i;
+    if (n1 > n2) {
+        T ratio = n1 / n2;
+        T sin2_t = sq(ratio) * (T(1) - sq(c));
+        if (sin2_t > T(1)) return T(1);
+        c = sqrt(T(1) - sin2_t);
+    }
+    T r0 = sq((n1 - n2) / (n1 + n2));
+    T x = T(1) - c;
+    T x5 = x * ((x * x) * (x * x));  // powi(5)
+    return fma(T(1) - r0, x5, r0);
+}
+
+// Material::resolve_color, material.rs:75-80, at the over point (material.rs:116-130)
+template <typename T, bool SMEM>
+RT_DEV V3<T> resolve_color(const SceneView<T, SMEM>& sv, uint32_t material, uint32_t pos, V3<T> over) {
+    const int pat = sv.material_pattern(material);
+    if (pat < 0) return ld3(sv.material(material));
+    V3<T> object_point = mat_point(sv.shape(pos), over);  // pattern.rs:10-14
+    V3<T> pattern_point = mat_point(sv.pattern((uint32_t)pat) + 6, object_point);
+    return pattern_color_at(sv, pat, pattern_point);
+}
+
+// Material::lighting, material.rs:53-114, for one light.  light_dir = normalized(light.position - over_point).
+// specular == 0 (every matte material): (intensity * 0) * pow(..) is an exact zero for the finite factor pow returns
+// on (0, ~1], so the whole term — and the pow call — is skipped.
+template <typename T>
+RT_DEV V3<T> phong_lighting(const T* m, V3<T> base, V3<T> intensity, V3<T> light_dir, V3<T> eye, V3<T> normal, bool in_shadow) {
+    V3<T> effective = hadamard(base, intensity);
+    V3<T> ambient = effective * m[MAT_AMBIENT];
+    if (in_shadow) return ambient;
+    T ldn = dot(light_dir, normal);
+    if (ldn < T(0)) return ambient;
+    V3<T> diffuse = (effective * m[MAT_DIFFUSE]) * ldn;
+    V3<T> refl = reflect(neg(light_dir), normal);
+    T rde = dot(refl, eye);
+    if (rde <= T(0) || m[MAT_SPECULAR] == T(0)) return ambient + diffuse;
+    T factor = pow(rde, m[MAT_SHININESS]);
+    V3<T> specular = (intensity * m[MAT_SPECULAR]) * factor;
+    return (ambient + diffuse) + specular;
+}
+
+// Canvas::to_png_file, canvas.rs:117-123: clamp to [0, 1], * 255, round half away from zero, NaN -> 0
+template <typename T>
+RT_DEV uint8_t quantise(T v) {
+    v = (v < T(0)) ? T(0) : v;
+    v = (v > T(1)) ? T(1) : v;
+    v = round(v * T(255));
+    return (v != v) ? (uint8_t)0 : (uint8_t)v;
+}
+
 // One frame of the explicit recursion stack = one World::shade_hit in flight (world.rs:38-67).
 template <typename T>
 struct Frame {
@@ -1198,15 +1290,8 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
                         state = ST_FETCH;  // padding slot: try again on the next round
                         if (x < cam.hsize && k < cam.n_rows) {
                             uint32_t y = ((k / cam.band_rows) * cam.shard_count + cam.shard_index) * cam.band_rows + k % cam.band_rows;
-                            // Camera::ray_for_pixel, camera.rs:52-68
-                            T offset_x = (T(x) + T(0.5)) * cam.pixel_size;
-                            T offset_y = (T(y) + T(0.5)) * cam.pixel_size;
-                            T world_x = cam.half_width - offset_x;
-                            T world_y = cam.half_height - offset_y;
-                            V3<T> pixel = mat_point(cam.inv, mk<T>(world_x, world_y, T(-1)));
-                            V3<T> origin = ld3(cam.origin);
-                            ray.o = origin;
-                            ray.d = normalized(pixel - origin);
+                            ray = camera_ray(cam, x, y);
+                            if (cam.probe_ray) ray.d = mk<T>(cam.inv[0], cam.inv[1], cam.inv[2]);
                             out_index = (size_t)(cam.out_full_frame ? y : k) * cam.hsize + x;
                             depth = 0;
                             state = ST_RADIANCE;
@@ -1275,9 +1360,7 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
                 hit_material = meta.y;
                 // Intersection::prepare_computations, intersection.rs:21-31
                 V3<T> point = ray.o + ray.d * t_hit;
-                V3<T> local_point = mat_point(g, point);  // shape.rs:22-27
-                V3<T> local_normal = local_normal_at(sv, (uint32_t)hit_pos, (meta.z >> FLAG_TYPE_SHIFT) & 7, g, local_point);
-                normal = normalized(mat_transposed_vector(g, local_normal));
+                normal = world_normal_at(sv, (uint32_t)hit_pos, (meta.z >> FLAG_TYPE_SHIFT) & 7, g, point);
                 eye = neg(ray.d);
                 if (dot(normal, eye) < T(0)) normal = neg(normal);
                 node_dir = ray.d;
@@ -1304,29 +1387,9 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
             // Material::lighting for light `light`, material.rs:53-114, evaluated at over_point (material.rs:116-130)
             const T* m = sv.material((uint32_t)hit_material);
             const T* lt = sv.light((uint32_t)light);
-            V3<T> intensity = ld3(lt + 3);
-            V3<T> effective = hadamard(base, intensity);
-            V3<T> ambient = effective * m[MAT_AMBIENT];
-            V3<T> lit = ambient;
-            bool in_shadow = acc.best_pos >= 0;
-            if (!in_shadow) {
-                V3<T> light_dir = normalized(ld3(lt) - over);
-                T ldn = dot(light_dir, normal);
-                if (!(ldn < T(0))) {
-                    V3<T> diffuse = (effective * m[MAT_DIFFUSE]) * ldn;
-                    V3<T> refl = reflect(neg(light_dir), normal);
-                    T rde = dot(refl, eye);
-                    // specular == 0 (every matte material): (intensity * 0) * pow(..) is an exact zero for the
-                    // finite factor pow returns on (0, ~1], so the whole term — and the pow call — is skipped
-                    if (rde <= T(0) || m[MAT_SPECULAR] == T(0)) {
-                        lit = ambient + diffuse;
-                    } else {
-                        T factor = pow(rde, m[MAT_SHININESS]);
-                        V3<T> specular = (intensity * m[MAT_SPECULAR]) * factor;
-                        lit = (ambient + diffuse) + specular;
-                    }
-                }
-            }
+            const bool in_shadow = acc.best_pos >= 0;
+            // the shadow ray's direction is normalized(light.position - over_point): the light vector of material.rs:88
+            const V3<T> lit = phong_lighting(m, base, ld3(lt + 3), ray.d, eye, normal, in_shadow);
             surface = surface + lit;  // fold(Color::BLACK, Color::add), world.rs:53
             ++light;
             if (light >= n_lights) after_lights = true;
@@ -1347,46 +1410,18 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
             }
             T cos_i = dot(eye, normal);
             if (remaining > 0 && m[MAT_TRANSPARENCY] != T(0)) {  // world.rs:136-154
-                T n_ratio = n1 / n2;
-                T sin2_t = sq(n_ratio) * (T(1) - sq(cos_i));
-                if (!(sin2_t > T(1))) {
-                    T cos_t = sqrt(T(1) - sin2_t);
+                T a, n_ratio;
+                if (refraction_coefficients(n1, n2, cos_i, a, n_ratio)) {
                     f.refr_o = under;
-                    f.refr_d = (normal * fma(n_ratio, cos_i, -cos_t)) - (eye * n_ratio);
+                    f.refr_d = (normal * a) - (eye * n_ratio);
                     f.flags |= FR_REFRACT;
                 }
             }
             if (m[MAT_REFLECTIVENESS] > T(0) && m[MAT_TRANSPARENCY] > T(0)) {  // world.rs:59
                 f.flags |= FR_SCHLICK;
-                // ComputedHit::schlicks_approximation, computed_hit.rs:50-68
-                T reflectance;
-                T c = cos_i;
-                bool total = false;
-                if (n1 > n2) {
-                    T ratio = n1 / n2;
-                    T sin2_t = sq(ratio) * (T(1) - sq(c));
-                    if (sin2_t > T(1)) total = true;
-                    else c = sqrt(T(1) - sin2_t);
-                }
-                if (total) {
-                    reflectance = T(1);
-                } else {
-                    T r0 = sq((n1 - n2) / (n1 + n2));
-                    T x = T(1) - c;
-                    T x5 = x * ((x * x) * (x * x));  // powi(5)
-                    reflectance = fma(T(1) - r0, x5, r0);
-                }
-                f.reflectance = reflectance;
+                f.reflectance = schlick_reflectance(n1, n2, cos_i);
             }
-            // Material::resolve_color, material.rs:75-80 (same for every light of this node)
-            int pat = sv.material_pattern((uint32_t)hit_material);
-            if (pat >= 0) {
-                V3<T> object_point = mat_point(sv.shape((uint32_t)hit_pos), over);  // pattern.rs:10-14
-                V3<T> pattern_point = mat_point(sv.pattern((uint32_t)pat) + 6, object_point);
-                base = pattern_color_at(sv, pat, pattern_point);
-            } else {
-                base = ld3(m);
-            }
+            base = resolve_color(sv, (uint32_t)hit_material, (uint32_t)hit_pos, over);  // the same for every light of this node
             surface = mk<T>(T(0), T(0), T(0));
             light = 0;
             if (n_lights == 0) after_lights = true;
@@ -1411,16 +1446,10 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
             if (returning) {
                 if (depth == 0) {  // Camera::render_parallel writes the pixel, camera.rs:108
                     if (out_rgb) store_rgb(out_rgb + out_index * 3, colour);
-                    if (out_rgb8) {  // Canvas::to_png_file, canvas.rs:117-123
-                        const T ch[3] = {colour.x, colour.y, colour.z};
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            T v = ch[k];
-                            v = (v < T(0)) ? T(0) : v;
-                            v = (v > T(1)) ? T(1) : v;
-                            v = round(v * T(255));
-                            out_rgb8[out_index * 3 + k] = (v != v) ? (uint8_t)0 : (uint8_t)v;
-                        }
+                    if (out_rgb8) {
+                        out_rgb8[out_index * 3 + 0] = quantise(colour.x);
+                        out_rgb8[out_index * 3 + 1] = quantise(colour.y);
+                        out_rgb8[out_index * 3 + 2] = quantise(colour.z);
                     }
                     state = ST_FETCH;
                     break;

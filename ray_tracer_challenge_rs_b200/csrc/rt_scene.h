@@ -112,6 +112,8 @@ struct CameraParams {
     uint32_t tile_stride;  // coprime to the number of 8x4 tiles: scattered tile order (rt_kernel.cuh)
     uint32_t out_full_frame;  // 1: outputs are full-frame buffers indexed by image row (zero-copy into the
                               //    caller's pinned host Canvas); 0: compact over the rows of this launch
+    uint32_t probe_ray;       // 1 (rtgpu_debug_color_at): every pixel's ray is (origin, inv[0..2]) as given, not normalised
+                              //    — World::color_at of an arbitrary ray through the unmodified kernels
 };
 
 // Work counters, in the order of the first six fields of rtgpu_stats.

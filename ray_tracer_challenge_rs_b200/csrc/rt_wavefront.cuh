@@ -88,16 +88,10 @@ struct WfCounts {
 template <typename T>
 RT_DEV void wf_store_pixel(T* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8, size_t out_index, V3<T> colour) {
     if (out_rgb) store_rgb(out_rgb + out_index * 3, colour);
-    if (out_rgb8) {  // Canvas::to_png_file, canvas.rs:117-123
-        const T ch[3] = {colour.x, colour.y, colour.z};
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            T v = ch[k];
-            v = (v < T(0)) ? T(0) : v;
-            v = (v > T(1)) ? T(1) : v;
-            v = round(v * T(255));
-            out_rgb8[out_index * 3 + k] = (v != v) ? (uint8_t)0 : (uint8_t)v;
-        }
+    if (out_rgb8) {
+        out_rgb8[out_index * 3 + 0] = quantise(colour.x);
+        out_rgb8[out_index * 3 + 1] = quantise(colour.y);
+        out_rgb8[out_index * 3 + 2] = quantise(colour.z);
     }
 }
 
@@ -223,14 +217,8 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                 active = x < cam.hsize && k < cam.n_rows;
                 if (active) {
                     const uint32_t y = ((k / cam.band_rows) * cam.shard_count + cam.shard_index) * cam.band_rows + k % cam.band_rows;
-                    // Camera::ray_for_pixel, camera.rs:52-68
-                    T offset_x = (T(x) + T(0.5)) * cam.pixel_size;
-                    T offset_y = (T(y) + T(0.5)) * cam.pixel_size;
-                    T world_x = cam.half_width - offset_x;
-                    T world_y = cam.half_height - offset_y;
-                    V3<T> pixel = mat_point(cam.inv, mk<T>(world_x, world_y, T(-1)));
-                    V3<T> origin = ld3(cam.origin);
-                    const V3<T> d = normalized(pixel - origin);
+                    const Ray<T> cr = camera_ray(cam, x, y);
+                    const V3<T> origin = cr.o, d = cam.probe_ray ? mk<T>(cam.inv[0], cam.inv[1], cam.inv[2]) : cr.d;
                     PK(PK_P + 0) = origin.x; PK(PK_P + 1) = origin.y; PK(PK_P + 2) = origin.z;
                     PK(PK_D + 0) = d.x; PK(PK_D + 1) = d.y; PK(PK_D + 2) = d.z;
                     out_index = (cam.out_full_frame ? y : k) * cam.hsize + x;
@@ -336,9 +324,7 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                     hit_material = meta.y;
                     const V3<T> P = mk<T>(PK(PK_P + 0), PK(PK_P + 1), PK(PK_P + 2)), D = mk<T>(PK(PK_D + 0), PK(PK_D + 1), PK(PK_D + 2));
                     V3<T> point = P + D * PK(PK_T_HIT);
-                    V3<T> local_point = mat_point(g, point);  // shape.rs:22-27
-                    V3<T> local_normal = local_normal_at(sv, (uint32_t)hit_pos, (meta.z >> FLAG_TYPE_SHIFT) & 7, g, local_point);
-                    V3<T> normal = normalized(mat_transposed_vector(g, local_normal));
+                    V3<T> normal = world_normal_at(sv, (uint32_t)hit_pos, (meta.z >> FLAG_TYPE_SHIFT) & 7, g, point);
                     if (dot(normal, neg(D)) < T(0)) normal = neg(normal);
                     PK(PK_NORMAL + 0) = normal.x; PK(PK_NORMAL + 1) = normal.y; PK(PK_NORMAL + 2) = normal.z;
                     // n1 / n2 only feed refracted_color and Schlick, both irrelevant without iterations left
@@ -365,47 +351,18 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                     if (remaining > 0 && m[MAT_REFLECTIVENESS] != T(0)) flags |= FR_REFLECT;  // world.rs:120
                     const T cos_i = dot(eye, normal);
                     if (remaining > 0 && m[MAT_TRANSPARENCY] != T(0)) {  // world.rs:136-154
-                        T n_ratio = n1 / n2;
-                        T sin2_t = sq(n_ratio) * (T(1) - sq(cos_i));
-                        if (!(sin2_t > T(1))) {
-                            T cos_t = sqrt(T(1) - sin2_t);
-                            PK(PK_REFR_A) = fma(n_ratio, cos_i, -cos_t);  // refracted direction = normal * a - eye * n_ratio (world.rs:150)
+                        T a, n_ratio;
+                        if (refraction_coefficients(n1, n2, cos_i, a, n_ratio)) {
+                            PK(PK_REFR_A) = a;  // refracted direction = normal * a - eye * n_ratio (world.rs:150)
                             PK(PK_REFR_N) = n_ratio;
                             flags |= FR_REFRACT;
                         }
                     }
                     if (m[MAT_REFLECTIVENESS] > T(0) && m[MAT_TRANSPARENCY] > T(0)) {  // world.rs:59
                         flags |= FR_SCHLICK;
-                        T c = cos_i;  // ComputedHit::schlicks_approximation, computed_hit.rs:50-68
-                        bool total = false;
-                        T reflectance;
-                        if (n1 > n2) {
-                            T ratio = n1 / n2;
-                            T sin2_t = sq(ratio) * (T(1) - sq(c));
-                            if (sin2_t > T(1)) total = true;
-                            else c = sqrt(T(1) - sin2_t);
-                        }
-                        if (total) {
-                            reflectance = T(1);
-                        } else {
-                            T r0 = sq((n1 - n2) / (n1 + n2));
-                            T x = T(1) - c;
-                            T x5 = x * ((x * x) * (x * x));  // powi(5)
-                            reflectance = fma(T(1) - r0, x5, r0);
-                        }
-                        PK(PK_REFLECTANCE) = reflectance;
+                        PK(PK_REFLECTANCE) = schlick_reflectance(n1, n2, cos_i);
                     }
-                    // Material::resolve_color, material.rs:75-80
-                    const int pat = sv.material_pattern((uint32_t)hit_material);
-                    V3<T> base;
-                    if (pat >= 0) {
-                        const V3<T> over = P + (normal * Real<T>::offset_eps());
-                        V3<T> object_point = mat_point(sv.shape((uint32_t)hit_pos), over);  // pattern.rs:10-14
-                        V3<T> pattern_point = mat_point(sv.pattern((uint32_t)pat) + 6, object_point);
-                        base = pattern_color_at(sv, pat, pattern_point);
-                    } else {
-                        base = ld3(m);
-                    }
+                    const V3<T> base = resolve_color(sv, (uint32_t)hit_material, (uint32_t)hit_pos, P + (normal * Real<T>::offset_eps()));
                     PK(PK_BASE + 0) = base.x; PK(PK_BASE + 1) = base.y; PK(PK_BASE + 2) = base.z;
                 }
             } else if (child < 0) {
@@ -413,28 +370,11 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                 if (alive) {
                     const T* lt = sv.light((uint32_t)light);
                     const T* m = sv.material((uint32_t)hit_material);
-                    V3<T> intensity = ld3(lt + 3);
                     const V3<T> base = mk<T>(PK(PK_BASE + 0), PK(PK_BASE + 1), PK(PK_BASE + 2));
                     const V3<T> normal = mk<T>(PK(PK_NORMAL + 0), PK(PK_NORMAL + 1), PK(PK_NORMAL + 2));
-                    V3<T> effective = hadamard(base, intensity);
-                    V3<T> ambient = effective * m[MAT_AMBIENT];
-                    V3<T> lit = ambient;
-                    if (!(acc.best_pos >= 0)) {
-                        V3<T> light_dir = tray.d;  // normalized(light.position - over_point), the shadow ray's direction
-                        T ldn = dot(light_dir, normal);
-                        if (!(ldn < T(0))) {
-                            V3<T> diffuse = (effective * m[MAT_DIFFUSE]) * ldn;
-                            V3<T> refl = reflect(neg(light_dir), normal);
-                            T rde = dot(refl, neg(mk<T>(PK(PK_D + 0), PK(PK_D + 1), PK(PK_D + 2))));
-                            if (rde <= T(0) || m[MAT_SPECULAR] == T(0)) {  // see render_kernel: an exact zero term
-                                lit = ambient + diffuse;
-                            } else {
-                                T factor = pow(rde, m[MAT_SHININESS]);
-                                V3<T> specular = (intensity * m[MAT_SPECULAR]) * factor;
-                                lit = (ambient + diffuse) + specular;
-                            }
-                        }
-                    }
+                    const V3<T> eye = neg(mk<T>(PK(PK_D + 0), PK(PK_D + 1), PK(PK_D + 2)));
+                    // the shadow ray's direction is normalized(light.position - over_point): the light vector of material.rs:88
+                    const V3<T> lit = phong_lighting(m, base, ld3(lt + 3), tray.d, eye, normal, acc.best_pos >= 0);
                     // fold(Color::BLACK, Color::add)
                     PK(PK_SURFACE + 0) += lit.x; PK(PK_SURFACE + 1) += lit.y; PK(PK_SURFACE + 2) += lit.z;
                 }

@@ -26,6 +26,7 @@
 #include "rt_bvh.h"
 #include "rt_kernel.cuh"
 #include "rt_wavefront.cuh"
+#include "rt_probe.cuh"
 #include "rt_scene.h"
 
 namespace {
@@ -946,6 +947,7 @@ int launch_kernel(rtgpu_context* ctx, const T* d_reals, const rt::CameraParams<T
 template <typename T>
 void fill_camera(const rtgpu_camera* c, const RowSel& rows, uint32_t n_rows, uint32_t max_depth, bool full_frame_out, rt::CameraParams<T>* out) {
     out->out_full_frame = full_frame_out ? 1u : 0u;
+    out->probe_ray = 0u;
     out->half_width = (T)c->half_width;
     out->half_height = (T)c->half_height;
     out->pixel_size = (T)c->pixel_size;
@@ -1707,6 +1709,67 @@ int rtgpu_render(const rtgpu_scene* scene, const rtgpu_camera* camera, const rtg
     }
     g_last_family = cache[0]->last_family;
     if (stats) stats->total_ms = wall_ms() - t0;
+    return RTGPU_OK;
+}
+
+int rtgpu_debug_probe(rtgpu_context* context, const rtgpu_camera* camera, uint32_t kind, const double* in, size_t n_in, double* out,
+                      size_t n_out) {
+    if (!context || !out || n_out == 0 || (n_in && !in)) return fail(RTGPU_ERR_INVALID_ARGUMENT, "context, in or out is NULL");
+    if (kind == RTGPU_PROBE_RAY_FOR_PIXEL && !camera) return fail(RTGPU_ERR_INVALID_ARGUMENT, "this probe needs a camera");
+    if (context->layout.n_bvh_nodes > 0 && (kind == RTGPU_PROBE_IN_SHADOW || kind == RTGPU_PROBE_PREPARE))
+        return fail(RTGPU_ERR_UNSUPPORTED, "scene queries through the probes cover uniform shape lists only (this scene uses a BVH)");
+    CUDA_TRY(cudaSetDevice(context->device));
+    rt::CameraParams<double> cam;
+    memset(&cam, 0, sizeof(cam));
+    if (camera) {
+        RowSel whole{camera->vsize ? camera->vsize : 1u, 0u, 1u};
+        fill_camera(camera, whole, camera->vsize, 6u, false, &cam);
+    }
+    double *d_in = nullptr, *d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_in, std::max<size_t>(1, n_in) * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&d_out, n_out * sizeof(double)));
+    if (n_in) CUDA_TRY(cudaMemcpy(d_in, in, n_in * sizeof(double), cudaMemcpyHostToDevice));
+    rt::SceneLayout lay = context->layout;
+    lay.in_shared = 0u;
+    rt::probe_kernel<double><<<1, 32, 0, context->stream>>>(context->d_reals64, context->d_ints, lay, cam, (int)kind, d_in, (int)n_in, d_out, (int)n_out);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(context->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, n_out * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(RTGPU_ERR_CUDA, "probe kernel failed: %s", cudaGetErrorString(e));
+    return RTGPU_OK;
+}
+
+int rtgpu_debug_color_at(rtgpu_context* context, const double origin[3], const double direction[3], const rtgpu_opts* opts, double out_rgb[3]) {
+    if (!context || !origin || !direction || !out_rgb) return fail(RTGPU_ERR_INVALID_ARGUMENT, "NULL argument");
+    uint32_t precision, max_depth;
+    int st = check_opts(opts, &precision, &max_depth);
+    if (st != RTGPU_OK) return st;
+    if (precision != RTGPU_PRECISION_F64) return fail(RTGPU_ERR_UNSUPPORTED, "colour probes run in the f64 parity mode");
+    CUDA_TRY(cudaSetDevice(context->device));
+    // a 1 x 1 frame whose only ray is the caller's, through the unmodified kernels of the requested family
+    rt::CameraParams<double> cam;
+    memset(&cam, 0, sizeof(cam));
+    cam.hsize = cam.vsize = cam.n_rows = cam.band_rows = 1u;
+    cam.shard_count = 1u;
+    cam.max_depth = max_depth;
+    cam.tile_stride = 0u;
+    cam.probe_ray = 1u;
+    for (int k = 0; k < 3; ++k) {
+        cam.origin[k] = origin[k];
+        cam.inv[k] = direction[k];
+    }
+    st = ensure_out_buffers(context, 3 * sizeof(double), 0);
+    if (st != RTGPU_OK) return st;
+    const int family = requested_family(opts) == FAMILY_WAVEFRONT ? FAMILY_WAVEFRONT : FAMILY_PERSISTENT;
+    context->last_family = g_last_family = family;
+    if (family == FAMILY_WAVEFRONT) st = render_wavefront<double>(context, context->d_reals64, cam, (double*)context->d_out, nullptr, nullptr, context->stream, true);
+    else if (max_depth <= 7) st = launch_kernel<double, 8>(context, context->d_reals64, cam, (double*)context->d_out, nullptr, nullptr, context->stream);
+    else st = launch_kernel<double, 16>(context, context->d_reals64, cam, (double*)context->d_out, nullptr, nullptr, context->stream);
+    if (st != RTGPU_OK) return st;
+    CUDA_TRY(cudaMemcpyAsync(out_rgb, context->d_out, 3 * sizeof(double), cudaMemcpyDeviceToHost, context->stream));
+    CUDA_TRY(cudaStreamSynchronize(context->stream));
     return RTGPU_OK;
 }
 
