@@ -209,9 +209,11 @@ uint32_t rtgpu_rows_list(const rtgpu_rows *rows, uint32_t vsize, uint32_t *out_r
  * (canvas.rs:117-123): clamp to [0,1], * 255, round half away from zero.  Either may be NULL, not
  * both.  Uses opts->n_gpus devices (row bands, no collective) and blocks until both host buffers
  * are complete.  `stats` may be NULL.
+ * Element type of out_rgb: `double` in RTGPU_PRECISION_F64 (hsize*vsize*3 doubles), `float` in
+ * RTGPU_PRECISION_F32 (hsize*vsize*3 floats) — hence `void *`; the same holds for rtgpu_context_render.
  */
 int rtgpu_render(const rtgpu_scene *scene, const rtgpu_camera *camera, const rtgpu_opts *opts,
-                 double *out_rgb, uint8_t *out_rgb8, rtgpu_stats *stats);
+                 void *out_rgb, uint8_t *out_rgb8, rtgpu_stats *stats);
 
 /* -- resident scene: what a caller rendering many frames / one rank of a multi-process job uses */
 int rtgpu_context_create(const rtgpu_scene *scene, int device, rtgpu_context **out_context);
@@ -235,7 +237,7 @@ int rtgpu_context_render_device(rtgpu_context *context, const rtgpu_camera *came
 /* Host-buffer variant on the resident scene: H2D of the camera, kernel, D2H of the selected rows
  * into the FULL-FRAME host buffers at their row offsets; blocks until done. */
 int rtgpu_context_render(rtgpu_context *context, const rtgpu_camera *camera, const rtgpu_opts *opts,
-                         const rtgpu_rows *rows, double *out_rgb, uint8_t *out_rgb8,
+                         const rtgpu_rows *rows, void *out_rgb, uint8_t *out_rgb8,
                          rtgpu_stats *stats);
 
 /* Kernel family the calling thread's most recent render ran: 0 = persistent, 1 = wavefront (what the automatic

@@ -1610,7 +1610,7 @@ int rtgpu_context_render_device(rtgpu_context* context, const rtgpu_camera* came
 int rtgpu_last_family(void) { return g_last_family; }
 
 int rtgpu_context_render(rtgpu_context* context, const rtgpu_camera* camera, const rtgpu_opts* opts, const rtgpu_rows* rows,
-                         double* out_rgb, uint8_t* out_rgb8, rtgpu_stats* stats) {
+                         void* out_rgb, uint8_t* out_rgb8, rtgpu_stats* stats) {
     if (!context || !camera) return fail(RTGPU_ERR_INVALID_ARGUMENT, "context or camera is NULL");
     if (!out_rgb && !out_rgb8) return fail(RTGPU_ERR_INVALID_ARGUMENT, "both output pointers are NULL");
     const double t0 = wall_ms();
@@ -1623,7 +1623,7 @@ int rtgpu_context_render(rtgpu_context* context, const rtgpu_camera* camera, con
     return RTGPU_OK;
 }
 
-int rtgpu_render(const rtgpu_scene* scene, const rtgpu_camera* camera, const rtgpu_opts* opts, double* out_rgb,
+int rtgpu_render(const rtgpu_scene* scene, const rtgpu_camera* camera, const rtgpu_opts* opts, void* out_rgb,
                  uint8_t* out_rgb8, rtgpu_stats* stats) {
     if (!camera) return fail(RTGPU_ERR_INVALID_ARGUMENT, "camera is NULL");
     if (!out_rgb && !out_rgb8) return fail(RTGPU_ERR_INVALID_ARGUMENT, "both output pointers are NULL");
