@@ -704,7 +704,7 @@ int requested_family(const rtgpu_opts* opts) {
 // Which family is faster depends on the scene (how much the per-pixel work varies) and on how many pixels one
 // launch covers, and no static rule we tried predicts it.  So FAMILY_AUTO measures: the first TUNE_RUNS frames of
 // each family for a given (scene, frame shape, path) are timed with CUDA events on the stream they run on,
-// alternating P, W, P, W; after that the faster family renders every frame.  Both families produce the same
+// alternating W, P, W, P; after that the faster family renders every frame.  Both families produce the same
 // pixels and counters bit for bit (tests/test_gpu_parity.py), so the choice is invisible apart from the time.
 constexpr int TUNE_RUNS = 2;
 
@@ -760,7 +760,11 @@ int resolve_family(rtgpu_context* ctx, const rtgpu_opts* opts, uint64_t key, boo
             return FAMILY_PERSISTENT;
         }
         *trial = true;
-        return (entry->runs[0] <= entry->runs[1] && entry->runs[0] < TUNE_RUNS) ? FAMILY_PERSISTENT : FAMILY_WAVEFRONT;
+        // Order W, P, W, P: the first frame of a (scene, frame shape) — all a one-shot CLI call ever renders — takes
+        // the family that wins on most scenes with secondary rays (cover, table, cylinders, reflect_refract, refraction;
+        // profiles/r2_notes.md), and with the small first-guess queues its cold start costs the same as the persistent
+        // kernel's (benchmarks/cold_one_shot.py).
+        return (entry->runs[FAMILY_WAVEFRONT] <= entry->runs[FAMILY_PERSISTENT] && entry->runs[FAMILY_WAVEFRONT] < TUNE_RUNS) ? FAMILY_WAVEFRONT : FAMILY_PERSISTENT;
     }
     return entry->best_ms[FAMILY_WAVEFRONT] < entry->best_ms[FAMILY_PERSISTENT] ? FAMILY_WAVEFRONT : FAMILY_PERSISTENT;
 }
@@ -787,13 +791,19 @@ void tune_end(rtgpu_context* ctx, cudaStream_t stream, uint64_t key, int family)
     ctx->tune_pending_key = key;
 }
 
+// First guess of the wavefront buffers per pixel of a launch.  The cover frame peaks at 0.63 queued hits and 1.5 node
+// records per pixel; glass-heavy frames ask for more and get it through the overflow -> enlarge -> render-again path,
+// once (the buffers are kept).  Small on purpose: the first frame of a process pays for allocating and first touching
+// them (3 + 5 per pixel = 1.7 GB at 1080p cost a cold call ~1 s and its first frame 15 ms instead of 2).
+constexpr double WF_RAYS_PER_PIXEL = 1.0, WF_NODES_PER_PIXEL = 2.0;
+
 template <typename T>
 int wavefront_reserve(rtgpu_context* ctx, uint64_t pixels, double growth) {
-    // first guess: 3 queued rays and 5 nodes per pixel; after an overflow the caller asks for more.
+    // first guess: WF_RAYS_PER_PIXEL queued rays and WF_NODES_PER_PIXEL nodes per pixel; after an overflow the caller asks for more.
     // RTGPU_WF_INITIAL_SCALE scales the guess (tests use a small one to exercise the enlarge-and-render-again path).
     if (const char* e = getenv("RTGPU_WF_INITIAL_SCALE"); growth == 1.0 && e && *e && atof(e) > 0.0) growth = atof(e);
-    size_t want_rays = std::max<size_t>((size_t)(3.0 * growth * (double)pixels), 1u << 12);
-    size_t want_nodes = std::max<size_t>((size_t)(5.0 * growth * (double)pixels), 1u << 12);
+    size_t want_rays = std::max<size_t>((size_t)(WF_RAYS_PER_PIXEL * growth * (double)pixels), 1u << 12);
+    size_t want_nodes = std::max<size_t>((size_t)(WF_NODES_PER_PIXEL * growth * (double)pixels), 1u << 12);
     want_rays = std::min<size_t>(want_rays, 0xFFFFFF00u);
     want_nodes = std::min<size_t>(want_nodes, 0x7FFFFF00u);
     const size_t bytes_rays = want_rays * sizeof(rt::WfRay<T>), bytes_nodes = want_nodes * sizeof(rt::WfNode<T>);
@@ -844,7 +854,7 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, level_kernel, RT_WF_THREADS, smem));
     if (blocks_per_sm < 1) return fail(RTGPU_ERR_CUDA, "wavefront kernel does not fit on an SM (smem %zu B)", smem);
     const uint64_t pixels = (uint64_t)cam.hsize * cam.n_rows;
-    if (ctx->wf_cap_rays == 0 || ctx->wf_bytes_rays / sizeof(rt::WfRay<T>) < 3 * pixels / 2) {
+    if (ctx->wf_cap_rays == 0 || (double)(ctx->wf_bytes_rays / sizeof(rt::WfRay<T>)) < WF_RAYS_PER_PIXEL * (double)pixels / 2) {
         int st = wavefront_reserve<T>(ctx, pixels, 1.0);
         if (st != RTGPU_OK) return st;
     }
@@ -919,8 +929,8 @@ int wavefront_check(rtgpu_context* ctx, uint64_t pixels, cudaStream_t stream, bo
     const rtgpu_context::HostStatus h = *ctx->h_status;
     if (!h.overflow) return 0;
     // what the frame actually asked for, with headroom
-    const double g_rays = (double)h.max_rays / (3.0 * (double)pixels), g_nodes = (double)h.n_nodes / (5.0 * (double)pixels);
-    const double growth = std::max(1.25 * std::max(g_rays, g_nodes), 2.0 * (double)ctx->wf_cap_rays / (3.0 * (double)pixels));
+    const double g_rays = (double)h.max_rays / (WF_RAYS_PER_PIXEL * (double)pixels), g_nodes = (double)h.n_nodes / (WF_NODES_PER_PIXEL * (double)pixels);
+    const double growth = std::max(1.25 * std::max(g_rays, g_nodes), 2.0 * (double)ctx->wf_cap_rays / (WF_RAYS_PER_PIXEL * (double)pixels));
     int st = wavefront_reserve<T>(ctx, pixels, growth);
     if (st != RTGPU_OK) return st;
     return 1;
@@ -1211,7 +1221,7 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
         // allocate the queues before the timed region (cudaMalloc waits for the device)
         const uint64_t pixels = (uint64_t)camera->hsize * n_rows;
         const size_t ray_bytes = precision == RTGPU_PRECISION_F64 ? sizeof(rt::WfRay<double>) : sizeof(rt::WfRay<float>);
-        if (ctx->wf_bytes_rays / ray_bytes < 3 * pixels / 2) {
+        if ((double)(ctx->wf_bytes_rays / ray_bytes) < WF_RAYS_PER_PIXEL * (double)pixels / 2) {
             st = precision == RTGPU_PRECISION_F64 ? wavefront_reserve<double>(ctx, pixels, 1.0) : wavefront_reserve<float>(ctx, pixels, 1.0);
             if (st == RTGPU_ERR_OUT_OF_MEMORY && forced_family < 0 && requested_family(opts) == FAMILY_AUTO) {
                 tune_rule_out_wavefront(ctx, key);

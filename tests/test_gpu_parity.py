@@ -424,7 +424,7 @@ def test_wavefront_shards_and_synthetic():
 
 
 def test_auto_family_measures_then_settles(monkeypatch):
-    """family=None: a context times two frames of each family (P, W, P, W), then keeps one; every frame is the
+    """family=None: a context times two frames of each family (W, P, W, P), then keeps one; every frame is the
     same bits whichever family rendered it.  Scenes without reflective / transparent materials never leave the
     persistent kernel."""
     monkeypatch.delenv("RTGPU_FAMILY", raising=False)
@@ -435,9 +435,9 @@ def test_auto_family_measures_then_settles(monkeypatch):
         frames = [r.render(cam) for _ in range(8)]
         other = [r.render(cam.resized(160, 90))[2]["family"] for _ in range(2)]  # another frame shape: measured afresh
     families = [st["family"] for _, _, st in frames]
-    assert families[:4] == ["persistent", "wavefront", "persistent", "wavefront"], families
+    assert families[:4] == ["wavefront", "persistent", "wavefront", "persistent"], families
     assert len(set(families[4:])) == 1, families
-    assert other == ["persistent", "wavefront"], other
+    assert other == ["wavefront", "persistent"], other
     for rgb, rgb8, st in frames[1:]:
         assert np.array_equal(rgb.view(np.uint64), frames[0][0].view(np.uint64))
         assert np.array_equal(rgb8, frames[0][1])
@@ -478,7 +478,7 @@ def test_auto_family_survives_without_room_for_the_queues(monkeypatch):
         with pytest.raises(abi.RtgpuError) as err:
             r.render(cam, family="wavefront")
         assert err.value.status == abi.ERR_OUT_OF_MEMORY
-    # room for the first guess (3 rays + 5 nodes per pixel = 283 MB at 512x512) but not for what this frame needs
+    # room for the first guess (1 ray + 2 nodes per pixel, two queues = 105 MB at 512x512) but not for what this frame needs
     # (23 rays per pixel: test_wavefront_equals_persistent_bit_for_bit relies on the same overflow)
     monkeypatch.delenv("RTGPU_WF_MAX_BYTES")
     monkeypatch.setenv("RTGPU_E2E_CHUNKS", "1")  # one launch sequence for the whole frame, as the sizes below assume
