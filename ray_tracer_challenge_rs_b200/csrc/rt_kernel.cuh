@@ -41,6 +41,9 @@ namespace rt {
 #ifndef RT_TMA_STAGE
 #define RT_TMA_STAGE 1  // scene tables -> shared memory by cp.async.bulk + mbarrier (0: plain loads).  Must precede stage_scene.
 #endif
+#ifndef RT_F32_OFFSET_ULPS
+#define RT_F32_OFFSET_ULPS 16  // f32 fast mode: over / under point offset in ulps of max(|point|, distance, 1); 8 .. 4096 swept in profiles/r2_notes.md
+#endif
 #ifndef RT_LEAN_LOOP
 #define RT_LEAN_LOOP 1  // trace_unified: pointer-driven shape loop with a single branch per culled shape
 #endif
@@ -63,15 +66,21 @@ struct Real;
 template <>
 struct Real<double> {
     static __device__ __forceinline__ double eps() { return 0.00000008; }  // consts.rs:2
-    static __device__ __forceinline__ double offset_eps() { return 0.00000008; }  // computed_hit.rs:33-34
+    // computed_hit.rs:33-34: over / under point = point +- normal * EPSILON, a constant
+    static __device__ __forceinline__ double offset(double, double, double, double) { return 0.00000008; }
     static __device__ __forceinline__ double max() { return DBL_MAX; }
     static __device__ __forceinline__ double cull_shrink() { return 1.0 - 1.0e-9; }  // >> f64 rounding of the pre-test
 };
 template <>
 struct Real<float> {
     static __device__ __forceinline__ float eps() { return 0.00000008f; }
-    // 8e-8 is below one f32 ulp at |x| >= 1: the fast mode needs its own offset.
-    static __device__ __forceinline__ float offset_eps() { return 1.0e-3f; }
+    // 8e-8 is below one f32 ulp at |x| >= 1: the fast mode needs its own offset, and a constant one is
+    // either too small far from the origin or too large for thin shapes: it scales with the magnitude of the hit
+    // point and of the hit distance (the rounding error of o + d * t is a few ulps of those), RT_F32_OFFSET_ULPS of them.
+    static __device__ __forceinline__ float offset(float px, float py, float pz, float t) {
+        const float scale = fmaxf(fmaxf(fmaxf(fabsf(px), fabsf(py)), fmaxf(fabsf(pz), fabsf(t))), 1.0f);
+        return (float)RT_F32_OFFSET_ULPS * 1.1920929e-7f * scale;
+    }
     static __device__ __forceinline__ float max() { return FLT_MAX; }
     static __device__ __forceinline__ float cull_shrink() { return 1.0f - 1.0e-3f; }
 };
@@ -478,7 +487,32 @@ template <typename T, int TYPE>
 RT_DEV int local_intersect(const Ray<T>& r, const T* g, int flags, const T* tri, T& t0, T& t1, T& t2, T& t3) {
     int n = 0;
     T ts[4] = {T(0), T(0), T(0), T(0)};
-    if (TYPE == 0) {  // shapes/sphere.rs:41-53
+    if (TYPE == 0 && sizeof(T) == 4) {
+        // f32 fast mode: b^2 - 4ac cancels catastrophically in binary32 when the origin is far away in object units
+        // (small or squashed spheres: shadow_puppets' 200 x 200 x 0.01 backdrop).  The discriminant is taken from the
+        // ray's closest approach to the centre instead (Haines et al., "Precision improvements for ray / sphere
+        // intersection"), and the roots from the stable pair q / a, c / q.  Not the reference's operations: this
+        // mode is bound by its stated tolerance, not bit parity.
+        const T a = dot(r.d, r.d);
+        const T bh = -dot(r.o, r.d);                   // half of -b
+        const T k = bh / a;
+        const V3<T> l = r.o + r.d * k;                 // closest point of the line to the centre
+        const T discr = T(1) - dot(l, l);              // x a = (b^2 - 4ac) / 4
+        if (!(discr < T(0))) {
+            const T c = dot(r.o, r.o) - T(1);
+            const T root = sqrt(a * discr);
+            const T q = bh + (bh < T(0) ? -root : root);
+            T s1 = q != T(0) ? c / q : T(0), s2 = q / a;
+            if (s1 > s2) {
+                const T tmp = s1;
+                s1 = s2;
+                s2 = tmp;
+            }
+            ts[0] = s1;
+            ts[1] = s2;
+            n = 2;
+        }
+    } else if (TYPE == 0) {  // shapes/sphere.rs:41-53
         T a = dot(r.d, r.d);
         T b = T(2) * dot(r.d, r.o);
         T c = dot(r.o, r.o) - T(1);
@@ -519,7 +553,23 @@ RT_DEV int local_intersect(const Ray<T>& r, const T* g, int flags, const T* tri,
             T b = T(2) * fma(r.o.x, r.d.x, r.o.z * r.d.z);
             T c = sq(r.o.x) + sq(r.o.z) - T(1);
             T d1, d2;
-            if (solve_quadratic(a, b, c, d1, d2)) {
+            bool roots;
+            if (sizeof(T) == 4) {
+                // f32 fast mode: the same closest-approach discriminant as the sphere's, in the xz plane
+                const T bh = -(r.o.x * r.d.x + r.o.z * r.d.z), k = bh / a;
+                const T lx = fma(r.d.x, k, r.o.x), lz = fma(r.d.z, k, r.o.z);
+                const T discr = T(1) - (lx * lx + lz * lz);
+                roots = !(discr < T(0));
+                if (roots) {
+                    const T root = sqrt(a * discr);
+                    const T q = bh + (bh < T(0) ? -root : root);
+                    d1 = q != T(0) ? c / q : T(0);
+                    d2 = q / a;
+                }
+            } else {
+                roots = solve_quadratic(a, b, c, d1, d2);
+            }
+            if (roots) {
                 if (d1 > d2) {
                     T t = d1;
                     d1 = d2;
@@ -1365,8 +1415,9 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
                 if (dot(normal, eye) < T(0)) normal = neg(normal);
                 node_dir = ray.d;
                 // computed_hit.rs:33-34
-                over = point + (normal * Real<T>::offset_eps());
-                under = point - (normal * Real<T>::offset_eps());
+                const T off = Real<T>::offset(point.x, point.y, point.z, t_hit);
+                over = point + (normal * off);
+                under = point - (normal * off);
                 const T* m = sv.material((uint32_t)hit_material);
                 // n1 / n2 feed refracted_color (world.rs:136, needs remaining > 0) and Schlick (world.rs:59,
                 // whose result multiplies black children when remaining == 0): only then walk containers

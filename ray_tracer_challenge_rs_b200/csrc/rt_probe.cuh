@@ -178,7 +178,8 @@ __global__ void probe_kernel(const T* __restrict__ g_reals, const int* __restric
         const V3<T> eye = neg(ray.d);
         const bool inside = dot(normal, eye) < T(0);
         if (inside) normal = neg(normal);
-        const V3<T> over = point + (normal * Real<T>::offset_eps()), under = point - (normal * Real<T>::offset_eps());
+        const T off = Real<T>::offset(point.x, point.y, point.z, t_hit);
+        const V3<T> over = point + (normal * off), under = point - (normal * off);
         // refraction containers (intersection.rs:33-62): the kernels' list-free bookkeeping — per shape, the parity of
         // its intersections before the hit and the last of them — fed with the CALLER's list, shape by shape, exactly
         // as the shape loop feeds it with what local_intersect returns.  (A hand-built list need not agree with the

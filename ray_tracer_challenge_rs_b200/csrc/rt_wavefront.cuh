@@ -276,7 +276,7 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                 if (spawn) {
                     const V3<T> P = mk<T>(PK(PK_P + 0), PK(PK_P + 1), PK(PK_P + 2));
                     const V3<T> normal = mk<T>(PK(PK_NORMAL + 0), PK(PK_NORMAL + 1), PK(PK_NORMAL + 2));
-                    const V3<T> off = normal * Real<T>::offset_eps();  // computed_hit.rs:33-34
+                    const V3<T> off = normal * Real<T>::offset(P.x, P.y, P.z, PK(PK_T_HIT));  // computed_hit.rs:33-34
                     if (child < 0) {  // World::is_in_shadow, world.rs:98-112
                         const V3<T> over = P + off;
                         Normalized<T> nl = normalize_full(ld3(sv.light((uint32_t)light)) - over);
@@ -362,7 +362,7 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                         flags |= FR_SCHLICK;
                         PK(PK_REFLECTANCE) = schlick_reflectance(n1, n2, cos_i);
                     }
-                    const V3<T> base = resolve_color(sv, (uint32_t)hit_material, (uint32_t)hit_pos, P + (normal * Real<T>::offset_eps()));
+                    const V3<T> base = resolve_color(sv, (uint32_t)hit_material, (uint32_t)hit_pos, P + (normal * Real<T>::offset(P.x, P.y, P.z, PK(PK_T_HIT))));
                     PK(PK_BASE + 0) = base.x; PK(PK_BASE + 1) = base.y; PK(PK_BASE + 2) = base.z;
                 }
             } else if (child < 0) {

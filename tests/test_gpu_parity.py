@@ -256,22 +256,35 @@ def test_multi_gpu_one_shot_is_byte_identical():
         assert np.array_equal(many.to_rgb8(), one.to_rgb8()), g
 
 
-F32_BARS = {  # fraction of pixels within 2 LSB of the f64 oracle that the f32 fast mode must reach
-    "three_sphere_scene": 0.995,
+# The f32 fast mode's STATED TOLERANCE (BASELINE.json north_star): the fraction of pixels whose
+# 8-bit output is within 2 LSB of the f64 oracle's, per shipped scene at 384 pixels wide.  Measured values are
+# 0.2 - 0.8 percentage points above these bars (profiles/r2_notes.md); the remaining outliers sit on silhouette and
+# shadow edges, and in `refraction` on paths through five nested glass spheres.
+F32_BARS = {
+    "three_sphere_scene": 0.9999,
+    "shadow_puppets": 0.999,
+    "cylinders": 0.998,
+    "metal": 0.9995,
+    "table": 0.999,
+    "reflect_refract": 0.999,
+    "refraction": 0.985,
+    "cover": 0.999,
 }
 
 
 @pytest.mark.parametrize("name", SHIPPED_SCENES)
 def test_f32_fast_mode_tolerance(name):
-    """f32 fast mode (own offset epsilon): stated tolerance per scene; always reported."""
+    """f32 fast mode (offset scaled to the hit point, closest-approach discriminants for spheres and cylinders;
+    SURVEY.md 0.6): the stated tolerance of every shipped scene is asserted, for both kernel families."""
     flat, camera = load_scene_fixture(name)
     cam = camera.resized(384, 384 * camera.vertical_size // camera.horizontal_size)
-    canvas = render_gpu(cam, flat, precision="f32")
     _, rgb8, _ = Oracle(flat).render(cam, want_rgb=False)
-    d = np.abs(canvas.to_rgb8().reshape(-1, 3).astype(int) - rgb8.astype(int)).max(axis=1)
-    frac = float((d <= 2).mean())
-    print(f"f32 {name}: {frac * 100:.3f}% within 2 LSB, max {int(d.max())}")
-    assert frac >= F32_BARS.get(name, 0.0), (name, frac)
+    for family in ("persistent", "wavefront"):
+        canvas = render_gpu(cam, flat, precision="f32", family=family)
+        d = np.abs(canvas.to_rgb8().reshape(-1, 3).astype(int) - rgb8.astype(int)).max(axis=1)
+        frac = float((d <= 2).mean())
+        print(f"f32 {name}: {frac * 100:.3f}% within 2 LSB, max {int(d.max())}")
+        assert frac >= F32_BARS[name], (name, family, frac)
 
 
 # ---------------------------------------------------------------------------------------------
