@@ -227,6 +227,7 @@ struct SceneView {
     RT_DEV int4 shape_meta(uint32_t pos) const { return reinterpret_cast<const int4*>(I())[(size_t)pos * (SHAPE_INTS / 4)]; }
     RT_DEV const T* triangle(uint32_t pos) const { return R() + L.tri_off + (size_t)I()[(size_t)pos * SHAPE_INTS + 4] * TRI_REALS; }
     RT_DEV const T* bvh_boxes(uint32_t node) const { return R() + L.bvh_off + (size_t)node * BVH_REALS; }
+    RT_DEV const float4* bvh_node32(uint32_t node) const { return reinterpret_cast<const float4*>(I() + L.bvh32_off) + (size_t)node * (BVH32_WORDS / 4); }
     RT_DEV int2 bvh_children(uint32_t node) const { return reinterpret_cast<const int2*>(I() + L.bvh_meta_off)[node]; }
     RT_DEV const T* material(uint32_t m) const { return R() + L.mat_off + (size_t)m * MAT_REALS; }
     RT_DEV int material_pattern(uint32_t m) const { return I()[L.mat_meta_off + m * MAT_INTS]; }
@@ -697,13 +698,58 @@ RT_DEV bool box_hit(const T* b, const Ray<T>& ray, V3<T> inv, T t_lo, T t_hi, T&
     return tn <= tf;
 }
 
+#ifndef RT_BVH_F32
+#define RT_BVH_F32 1  // box tests in single precision with rigorous margins (0: in T, as in round 1)
+#endif
+
+// The ray as the single-precision box test sees it.  Every quantity errs on the side of a LARGER parameter interval:
+//   o_plus / o_minus  the origin moved by delta = 2^-21 * max(|o|, largest box coordinate) towards +inf / -inf: more
+//                     than the rounding of the origin to float plus that of the subtraction below, so
+//                     lo_f - o_plus <= lo - o and hi_f - o_minus >= hi - o hold in exact arithmetic (lo_f <= lo and
+//                     hi_f >= hi: the packer rounds the boxes outwards);
+//   inv               1 / d rounded to float (relative error 2^-24; +-inf for a zero component);
+// products and the conversion of the query's distance bounds add relative errors below 2^-22, which the final
+// comparison absorbs with a relative slack of 2^-20.
+struct BoxRay32 {
+    float opx, opy, opz, omx, omy, omz, ix, iy, iz;
+};
+template <typename T>
+RT_DEV BoxRay32 make_box_ray(const Ray<T>& ray, float coord_max) {
+    BoxRay32 b;
+    const float ox = (float)ray.o.x, oy = (float)ray.o.y, oz = (float)ray.o.z;
+    const float delta = 4.76837158e-7f * fmaxf(fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fabsf(oz)), coord_max);
+    b.opx = ox + delta; b.opy = oy + delta; b.opz = oz + delta;
+    b.omx = ox - delta; b.omy = oy - delta; b.omz = oz - delta;
+    b.ix = (float)(T(1) / ray.d.x); b.iy = (float)(T(1) / ray.d.y); b.iz = (float)(T(1) / ray.d.z);
+    return b;
+}
+// lo / hi: one child's box (outward-rounded floats); [t_lo, t_hi]: the distances the query still cares about, already
+// rounded outwards.  fminf / fmaxf drop the NaN of 0 * inf (origin on a widened plane of a slab the ray is parallel
+// to: outside the true box).
+RT_DEV bool box_hit32(float lox, float loy, float loz, float hix, float hiy, float hiz, const BoxRay32& r, float t_lo, float t_hi, float& enter) {
+    const float x1 = (lox - r.opx) * r.ix, x2 = (hix - r.omx) * r.ix;
+    const float y1 = (loy - r.opy) * r.iy, y2 = (hiy - r.omy) * r.iy;
+    const float z1 = (loz - r.opz) * r.iz, z2 = (hiz - r.omz) * r.iz;
+    const float tn = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fmaxf(fminf(z1, z2), t_lo));
+    const float tf = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fminf(fmaxf(z1, z2), t_hi));
+    enter = tn;
+    return tn <= 3.4028235e38f && tn - tf <= 9.5367432e-7f * (fabsf(tn) + fabsf(tf));
+}
+RT_DEV float float_up(double v) { return __double2float_ru(v); }
+RT_DEV float float_up(float v) { return v; }
+
 template <typename T, bool FULL, bool SMEM>
 RT_DEV void trace_bvh(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
     const bool active = acc.mode != MODE_IDLE;
+#if RT_BVH_F32
+    const BoxRay32 bray = make_box_ray(ray, sv.L.bvh_coord_max);
+    const float t_lo32 = (acc.mode == MODE_CONTAINER) ? -3.4028235e38f : 0.0f;
+#else
     // 1 / d per axis; only used for the conservative box tests, so plain reciprocals are enough.
     // A zero component gives +-inf, which the slab test handles.
     V3<T> inv = mk<T>(T(1) / ray.d.x, T(1) / ray.d.y, T(1) / ray.d.z);
     const T t_lo = (acc.mode == MODE_CONTAINER) ? -Real<T>::max() : T(0);
+#endif
     int stack[BVH_MAX_DEPTH + 4];
     int sp = 0;
     int cur = active ? 0 : INT_MIN;  // INT_MIN = nothing left to visit; >= 0 inner node; < 0 leaf ~pos
@@ -731,12 +777,22 @@ RT_DEV void trace_bvh(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<
                 cur = sp > 0 ? stack[--sp] : INT_MIN;
                 break;
             }
+#if RT_BVH_F32
+            const float4* nd = sv.bvh_node32((uint32_t)cur);
+            const float4 n0 = nd[0], n1 = nd[1], n2 = nd[2];
+            const int2 ch = make_int2(__float_as_int(nd[3].x), __float_as_int(nd[3].y));
+            const float t_hi32 = float_up((acc.mode == MODE_CONTAINER) ? acc.c->t_hit : acc.best_t);
+            float e0, e1;
+            const bool h0 = box_hit32(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, bray, t_lo32, t_hi32, e0);
+            const bool h1 = box_hit32(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, bray, t_lo32, t_hi32, e1);
+#else
             const T* nb = sv.bvh_boxes((uint32_t)cur);
             const int2 ch = sv.bvh_children((uint32_t)cur);
             const T t_hi = (acc.mode == MODE_CONTAINER) ? acc.c->t_hit : acc.best_t;
             T e0, e1;
             const bool h0 = box_hit(nb, ray, inv, t_lo, t_hi, e0);
             const bool h1 = box_hit(nb + 6, ray, inv, t_lo, t_hi, e1);
+#endif
             if (h0 && h1) {
                 const bool near0 = e0 <= e1;
                 stack[sp++] = near0 ? ch.y : ch.x;

@@ -77,6 +77,12 @@ constexpr int CULL_REALS = 4;
 // < 0 the leaf shape at sorted position ~ref.  One shape per leaf.
 constexpr int BVH_REALS = 12;
 constexpr int BVH_INTS = 2;
+// The traversal reads a single-precision copy of the node: 16 words = 64 bytes, 16-byte aligned, in the int blob:
+//   [0..11] the two children's boxes as floats ROUNDED OUTWARDS from the double boxes (lo[3], hi[3] each),
+//   [12..13] the child references, [14..15] unused.
+// The box test is a conservative filter (rt_kernel.cuh box_hit32): single precision with rigorous margins costs a
+// quarter of the instructions of the double test and halves the bytes per node visit.
+constexpr int BVH32_WORDS = 16;
 constexpr int BVH_MAX_DEPTH = 60;  // device traversal stack; the builder falls back to median splits to stay below
 
 constexpr int NUM_SHAPE_TYPES = 6;  // order = rtgpu_shape_type: sphere, plane, cube, cylinder, cone, triangle
@@ -88,6 +94,8 @@ struct SceneLayout {
     uint32_t n_materials, n_patterns, n_lights;
     uint32_t tri_off, mat_off, pat_off, light_off, cull_off, bvh_off;  // offsets into the real blob, in reals
     uint32_t mat_meta_off, pat_meta_off, bvh_meta_off;  // offsets into the int blob, in int32
+    uint32_t bvh32_off;                             // single-precision BVH nodes (BVH32_WORDS each), int blob, multiple of 4
+    float bvh_coord_max;                            // largest |coordinate| of any BVH box (sizes the origin margin of box_hit32)
     uint32_t n_bvh_nodes;                           // > 0: the bounded shapes are reached through a BVH
     int32_t bvh_root;                               // root reference (>= 0 node, < 0 single leaf)
     uint32_t n_reals, n_ints;                       // blob sizes

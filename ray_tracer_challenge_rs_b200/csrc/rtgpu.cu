@@ -307,7 +307,8 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
         n_bounded += bounded[i];
     }
     const uint32_t threshold = bvh_threshold();
-    const bool use_bvh = threshold > 0 && n_bounded >= threshold;
+    // (a hierarchy over a single shape would be one half-empty node whose empty box no slab test rejects: keep it flat)
+    const bool use_bvh = threshold > 0 && n_bounded >= std::max(threshold, 2u);
     // flat part: stable grouping by type, world order kept inside a type (and carried as `orig` for tie-breaks)
     std::vector<uint32_t> order;
     order.reserve(S);
@@ -365,7 +366,8 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     lay.mat_meta_off = S * rt::SHAPE_INTS;
     lay.pat_meta_off = lay.mat_meta_off + M * rt::MAT_INTS;
     lay.bvh_meta_off = (lay.pat_meta_off + Q * rt::PAT_INTS + 1u) & ~1u;
-    lay.n_ints = lay.bvh_meta_off + lay.n_bvh_nodes * rt::BVH_INTS;
+    lay.bvh32_off = (lay.bvh_meta_off + lay.n_bvh_nodes * rt::BVH_INTS + 3u) & ~3u;
+    lay.n_ints = lay.bvh32_off + lay.n_bvh_nodes * rt::BVH32_WORDS;
     lay.n_ints = (lay.n_ints + 3u) & ~3u;
     if ((uint64_t)S * rt::SHAPE_REALS + (uint64_t)n_tri * rt::TRI_REALS + (uint64_t)S * rt::CULL_REALS + (uint64_t)lay.n_bvh_nodes * rt::BVH_REALS > 0xF0000000ull)
         return fail(RTGPU_ERR_UNSUPPORTED, "scene too large for 32-bit blob offsets (%u shapes)", S);
@@ -455,6 +457,29 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
             I[lay.bvh_meta_off + k * rt::BVH_INTS + 0] = leaf_ref(bvh.nodes[k].child[0]);
             I[lay.bvh_meta_off + k * rt::BVH_INTS + 1] = leaf_ref(bvh.nodes[k].child[1]);
         }
+    }
+    if (use_bvh) {
+        // single-precision node copies: boxes rounded outwards, children alongside (rt_scene.h BVH32_WORDS)
+        auto down = [](double v) { float f = (float)v; return ((double)f > v) ? std::nextafterf(f, -std::numeric_limits<float>::infinity()) : f; };
+        auto up = [](double v) { float f = (float)v; return ((double)f < v) ? std::nextafterf(f, std::numeric_limits<float>::infinity()) : f; };
+        float coord_max = 0.0f;
+        for (uint32_t k = 0; k < lay.n_bvh_nodes; ++k) {
+            const double* nb = R + lay.bvh_off + (size_t)k * rt::BVH_REALS;
+            int* w = I + lay.bvh32_off + (size_t)k * rt::BVH32_WORDS;
+            float f[12];
+            for (int c = 0; c < 2; ++c)
+                for (int a = 0; a < 3; ++a) {
+                    f[c * 6 + a] = down(nb[c * 6 + a]);
+                    f[c * 6 + 3 + a] = up(nb[c * 6 + 3 + a]);
+                }
+            for (int j = 0; j < 12; ++j)
+                if (std::isfinite(f[j])) coord_max = std::max(coord_max, std::fabs(f[j]));
+            memcpy(w, f, sizeof(f));
+            w[12] = I[lay.bvh_meta_off + k * rt::BVH_INTS + 0];
+            w[13] = I[lay.bvh_meta_off + k * rt::BVH_INTS + 1];
+            w[14] = w[15] = 0;
+        }
+        lay.bvh_coord_max = coord_max;
     }
     // FNV-1a over (a sample of) the blobs: tells the family tuner whether two uploads are the same scene
     uint64_t fp = 1469598103934665603ull;
