@@ -149,14 +149,38 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def synthetic_shapes(args) -> int:
+    """--scene synthetic:<N> = BASELINE.json configs[4]: N spheres + triangles with random materials and patterns."""
+    return int(args.scene.split(":", 1)[1]) if args.scene.startswith("synthetic:") else 0
+
+
 def load_workload(args):
+    if synthetic_shapes(args):
+        from ray_tracer_challenge_rs_b200.synthetic import synthetic_camera, synthetic_scene
+
+        return synthetic_scene(synthetic_shapes(args)), synthetic_camera(args.width, args.height)
     from ray_tracer_challenge_rs_b200.fixtures import load_scene_fixture
 
     flat, camera = load_scene_fixture(args.scene)
     return flat, camera.resized(args.width, args.height)
 
 
+def oracle_sample(args, flat, camera):
+    """Pixels the CPU arm renders per step: the whole frame for the shipped scenes; for the synthetic scene (brute
+    force over N shapes per ray: a whole 8K frame of 10^5 shapes is a day of CPU time) a fixed pseudo-random sample
+    sized for ~10 s on 16+ cores.  None = whole frame."""
+    n = synthetic_shapes(args)
+    if not n:
+        return None
+    total = camera.horizontal_size * camera.vertical_size
+    count = int(min(total, max(512, 4.0e8 / n)))
+    return np.random.default_rng(0xB200).choice(total, size=count, replace=False).astype(np.uint64)
+
+
 def data_label(args) -> str:
+    if synthetic_shapes(args):
+        return (f"synthetic: {synthetic_shapes(args)} spheres + triangles with random materials and patterns, two lights (numpy PCG64, seed 0xB200; "
+                "ray_tracer_challenge_rs_b200/synthetic.py) — BASELINE.json configs[4]")
     return (f"the reference's shipped scenes/{args.scene}.yaml (committed flattened fixture of the YAML), camera resized to "
             f"{args.width}x{args.height}; no dataset, no random geometry")
 
@@ -169,9 +193,11 @@ def quantise_rgb8(rgb: np.ndarray) -> np.ndarray:
 
 
 def workload_config(args, flat, extra=None) -> dict:
+    what = (f"synthetic scaling scene, {synthetic_shapes(args)} shapes" if synthetic_shapes(args) else f"{args.scene}.yaml")
+    which = "configs[4]" if synthetic_shapes(args) else "configs[1]" if (args.scene, args.width, args.height) == ("cover", 1920, 1080) else "configs[2..3]"
     cfg = {
-        "workload": f"{args.scene}.yaml @ {args.width}x{args.height}, {args.precision} {'parity' if args.precision == 'f64' else 'fast'} mode, "
-                    f"max recursion depth {args.max_depth} (BASELINE.json configs[1])",
+        "workload": f"{what} @ {args.width}x{args.height}, {args.precision} {'parity' if args.precision == 'f64' else 'fast'} mode, "
+                    f"max recursion depth {args.max_depth} (BASELINE.json {which})",
         "scene": args.scene, "width": args.width, "height": args.height, "precision": args.precision,
         "max_depth": args.max_depth, "shapes": flat.shape_counts(), "lights": flat.n_lights,
         "cache": "scene tables are ~3 KB staged in shared memory and the 50 MB frame is write-only, so L2 contents cannot help a step; "
@@ -195,11 +221,23 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def time_oracle(flat, camera, max_depth: int, steps: int, warmup: int, threads: int = 0):
+def time_oracle(flat, camera, max_depth: int, steps: int, warmup: int, threads: int = 0, pixels=None):
+    """Times the CPU oracle.  pixels = None: whole frames (returns the f64 frame); else only those pixel indices
+    (returns their colours)."""
     from oracle import oracle as O
 
     if threads <= 0:
         threads = host_threads()
+    if pixels is not None:
+        orc = O.Oracle(flat)
+        times, rgb, st = [], None, None
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            rgb, _, st = orc.render_pixels(camera, pixels, max_depth=max_depth, threads=threads)
+            t1 = time.perf_counter()
+            if i >= warmup:
+                times.append(t1 - t0)
+        return times, st, threads, rgb
 
     orc = O.Oracle(flat)
     n = camera.horizontal_size * camera.vertical_size
@@ -241,16 +279,19 @@ def run_reference(args):
     if rank != 0:
         return  # the CPU arm runs once, on rank 0
     flat, camera = load_workload(args)
-    times, stats, cores, _ = time_oracle(flat, camera, args.max_depth, args.steps, args.warmup)
+    sample = oracle_sample(args, flat, camera)
+    times, stats, cores, _ = time_oracle(flat, camera, args.max_depth, args.steps, args.warmup, pixels=sample)
     total = sum(times)
     mrays = stats["rays"] * len(times) / total / 1e6
+    sample_text = (f"the whole {args.width}x{args.height} frame" if sample is None else
+                   f"{sample.size} pseudo-random pixels of the {args.width}x{args.height} frame (brute force over {flat.n_shapes} shapes per ray)")
     line = {
         "impl": "reference", "metric": METRIC, "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": data_label(args),
         "config": workload_config(args, flat),
         "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                         "sample": f"the whole {args.width}x{args.height} frame, {len(times)} times; restated reference (C + OpenMP, "
+                         "sample": f"{sample_text}, {len(times)} times; restated reference (C + OpenMP, "
                                    "-ffp-contract=off), not rustc output — no Rust toolchain in this image",
                          "ms_per_frame": total / len(times) * 1e3, "best_ms_per_frame": min(times) * 1e3},
         "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -267,13 +308,19 @@ RESULT_LINE = []  # filled by the arm that ran; printed by main() once stdout is
 CALIBRATION_FRAMES = 4  # 2 per kernel family (TUNE_RUNS in csrc/rtgpu.cu)
 
 
+PROFILED_TRAFFIC = {  # (scene, width, height, precision, depth, family) -> committed ncu per-launch list of one frame
+    ("cover", 1920, 1080, "f64", 6, "wavefront"): "profiles/r2b_wavefront_launches.csv",
+    ("synthetic:100000", 7680, 4320, "f64", 6, "wavefront"): "profiles/r2_synthetic_1e5_8k_launches.csv",
+}
+
+
 def profiled_traffic(args, family: str):
     """DRAM bytes per frame (dram__bytes_read.sum + dram__bytes_write.sum over all launches of one frame) from the
-    committed ncu launch list, for the configuration it was captured on; None for anything else."""
-    if (args.scene, args.width, args.height, args.precision, args.max_depth, family) != ("cover", 1920, 1080, "f64", 6, "wavefront"):
-        return None, None
-    path = os.path.join(ROOT, "profiles", "r1_wavefront_launches.csv")
-    if not os.path.exists(path):
+    committed ncu launch list, for the configurations one was captured on; None for anything else.  (A profiler
+    cannot run inside the timed bench: `traffic_model` beside it is computed in-run from the device's record counts.)"""
+    rel = PROFILED_TRAFFIC.get((args.scene, args.width, args.height, args.precision, args.max_depth, family))
+    path = os.path.join(ROOT, rel) if rel else None
+    if not path or not os.path.exists(path):
         return None, None
     import csv
 
@@ -283,7 +330,16 @@ def profiled_traffic(args, family: str):
             if len(r) > 10 and r[-3] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[-2], 1.0)
                 total += float(r[-1].replace(",", "")) * scale
-    return (total or None), "profiles/r1_wavefront_launches.csv (ncu, every launch of one frame)"
+    return (total or None), f"{rel} (ncu, every launch of one frame)"
+
+
+def hbm_peak_gbs():
+    """MEASURED_PEAKS.json (driver-written) if present, else the profiling recipe's fallback for B200."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6550.0, "B200_PROFILING.md fallback (measured copy bandwidth of this pool's B200s)"
 
 
 def launches_per_frame(family: str, max_depth: int) -> int:
@@ -401,6 +457,14 @@ def run_b200(args):
                 frame_device[np.asarray(row_ids, dtype=np.int64)] = shard.reshape(len(row_ids), camera.horizontal_size, 3)
             frame_device = frame_device.reshape(-1, 3)
 
+    # ---- what the wavefront family moved through HBM for one frame: record counts from the device (all ranks) ----
+    records = {"queued_rays": 0, "node_records": 0, "ray_record_bytes": 0, "node_record_bytes": 0}
+    if family_used == "wavefront":
+        renderer.render(camera, precision=args.precision, max_depth=args.max_depth, rows=rows, want_rgb8=False, family="wavefront")
+        records = renderer.frame_records()
+    summed = sum_over_ranks([float(records["queued_rays"]), float(records["node_records"])])
+    records["queued_rays"], records["node_records"] = int(summed[0]), int(summed[1])
+
     # ---- end to end through the reference-facing call, host buffers (rank 0 drives all N devices) ----
     n_px = camera.horizontal_size * camera.vertical_size
     e2e = None
@@ -454,37 +518,70 @@ def run_b200(args):
         peak_tflops, _ = measure_fma_peak(args.precision, device=local_rank)
         flops = frame_flops(flat, stats)  # whole frame, all ranks
         traffic, traffic_source = profiled_traffic(args, family_used)
+        # in-run model of the same traffic: every queued hit is one ray record written and read once, every node record
+        # is written once and read once by the combine pass, every child colour is one 24-byte slot write, and the
+        # frame is written once (counts from this run's device counters; record sizes from the library)
+        traffic_model = (2.0 * records["queued_rays"] * records["ray_record_bytes"] + 2.0 * records["node_records"] * records["node_record_bytes"] +
+                         records["queued_rays"] * 3.0 * elem + n_px * 3.0 * elem)
+        hbm_peak, hbm_peak_source = hbm_peak_gbs()
         achieved = flops / world / (device_ms / K * 1e-3) / 1e12  # per device: each renders 1/N of the frame in device_ms/K
         roofline = {
             "bound": "fp64_fma_pipe" if args.precision == "f64" else "fp32_fma_pipe", "achieved": achieved, "peak": peak_tflops,
             "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": traffic, "traffic_source": traffic_source,
-            "kernel": "rt::wf_level_kernel x (max_depth + 1) = 93 % of the step (profiles/r1_wavefront_launches.md); achieved = "
+            "kernel": "rt::wf_level_kernel x (max_depth + 1) = 90 % of the step (profiles/r2_wavefront_launches.md); achieved = "
                       "frame flops / frame time" if family_used == "wavefront" else "rt::render_kernel (the whole step)",
             "peak_source": "measured live: 8 independent FMA chains per thread on every SM (rtgpu_measure_fma_peak); "
                            "MEASURED_PEAKS.json holds only HBM and bf16 peaks",
             "algorithmic_flops_per_frame": flops, "flops_per_ray": flops_per_ray(flat),
-            "hbm_note": f"frame write {n_px * 3 * elem / 1e6:.1f} MB per step = "
-                        f"{n_px * 3 * elem / (device_ms / K * 1e-3) / 1e9 / world:.1f} GB/s per device: HBM is not the bound",
+            "traffic_model": traffic_model, "traffic_model_source": "in-run: device record counts (rtgpu_context_frame_records) x record sizes + the frame write",
+            "hbm": {"achieved_gbs": (traffic or traffic_model) / (device_ms / K * 1e-3) / 1e9 / world, "peak_gbs": hbm_peak, "peak_source": hbm_peak_source,
+                    "frac": (traffic or traffic_model) / (device_ms / K * 1e-3) / 1e9 / world / hbm_peak,
+                    "note": "HBM is not the bound of this path: scene tables sit in shared memory / L2 (BVH scenes: L2 hit rate 84-91 %, "
+                            "profiles/r2_notes.md); the traffic is queue and node records plus the frame write"},
         }
+        if synthetic_shapes(args):
+            roofline["note"] = ("algorithmic flops = the reference's brute force over every shape per ray (SURVEY 8d convention); the BVH skips almost all "
+                                "of it, so `frac` says how much faster than a brute-force FP64 machine at peak the frame ran, not pipe utilisation")
         # ---- CPU baseline beside it (bounded: 3 frames) ----
-        cpu = None
+        cpu, cold = None, None
         if world == 1:  # the CPU leg runs at N = 1 only (the other N reuse the reference arm the driver runs beside this one)
-            times, ostats, cores, oracle_rgb = time_oracle(flat, camera, args.max_depth, steps=3, warmup=1)
-            serial_mrays, serial_px = time_oracle_serial_sample(flat, camera, args.max_depth)
-            cpu = {"value": ostats["rays"] / min(times) / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                   "sample": f"the same whole {args.width}x{args.height} frame, best of 3; restated reference (C + OpenMP), not rustc output",
-                   "ms_per_frame": min(times) * 1e3,
-                   "serial": {"value": serial_mrays, "unit": "Mrays/s", "cores": 1, "sample": f"every 16th pixel of the frame ({serial_px} pixels), one thread"}}
-            # parity against the oracle's frame of the same run: 8-bit output, and the work counters in parity mode
-            dev8, ora8 = quantise_rgb8(frame_device.astype(np.float64)), quantise_rgb8(oracle_rgb)
+            sample = oracle_sample(args, flat, camera)
+            if sample is None:
+                times, ostats, cores, oracle_rgb = time_oracle(flat, camera, args.max_depth, steps=3, warmup=1)
+                serial_mrays, serial_px = time_oracle_serial_sample(flat, camera, args.max_depth)
+                cpu = {"value": ostats["rays"] / min(times) / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                       "sample": f"the same whole {args.width}x{args.height} frame, best of 3; restated reference (C + OpenMP), not rustc output",
+                       "ms_per_frame": min(times) * 1e3,
+                       "serial": {"value": serial_mrays, "unit": "Mrays/s", "cores": 1, "sample": f"every 16th pixel of the frame ({serial_px} pixels), one thread"}}
+                device_rgb = frame_device
+            else:
+                times, ostats, cores, oracle_rgb = time_oracle(flat, camera, args.max_depth, steps=1, warmup=0, pixels=sample)
+                cpu = {"value": ostats["rays"] / min(times) / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                       "sample": f"{sample.size} pseudo-random pixels of the frame, once (brute force over {flat.n_shapes} shapes per ray); restated reference "
+                                 "(C + OpenMP), not rustc output",
+                       "seconds": min(times), "whole_frame_estimate_s": rays / (ostats["rays"] / min(times))}
+                device_rgb = frame_device[sample.astype(np.int64)]
+                frame_id["oracle_sample_pixels"] = int(sample.size)
+            # parity against the oracle's pixels of the same run: 8-bit output, and the work counters in parity mode
+            dev8, ora8 = quantise_rgb8(device_rgb.astype(np.float64)), quantise_rgb8(oracle_rgb)
             diff = np.abs(dev8.astype(np.int16) - ora8.astype(np.int16)).max(axis=1)
             frame_id["rgb8_pixels_differing_from_oracle"] = int((diff > 0).sum())
             frame_id["rgb8_pixels_beyond_1lsb"] = int((diff > 1).sum())
             frame_id["oracle_rgb8_sha256"] = sha(ora8)
             frame_id["rgb8_sha256"] = sha(dev8)
             if args.precision == "f64":  # parity mode: the device ray count is integer-equal to the oracle's
-                assert ostats["rays"] == rays, (ostats, stats)
+                assert sample is not None or ostats["rays"] == rays, (ostats, stats)
                 assert frame_id["rgb8_pixels_differing_from_oracle"] == 0, frame_id
+            # ---- cold one-shot: a fresh process's first rtgpu_render (the region ray-tracer-cli/src/main.rs:17-22 times) ----
+            if not args.no_cold and not synthetic_shapes(args):
+                try:
+                    out = subprocess.run([sys.executable, os.path.join(ROOT, "benchmarks", "cold_one_shot.py"), "--child", "--scene", args.scene, "--width",
+                                          str(args.width), "--height", str(args.height), "--family", "auto"], capture_output=True, text=True, timeout=300)
+                    cold = json.loads(out.stdout.strip().splitlines()[-1])
+                    cold["note"] = ("fresh process, scene already loaded, pageable numpy Canvas: CUDA driver + context creation and module load dominate "
+                                    "(0.4 - 4 s on these boxes, profiles/r2_notes.md); steady state is `e2e`")
+                except Exception as exc:  # the cold probe must never cost the bench line
+                    cold = {"error": repr(exc)}
         line = {
             "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": device_ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -493,7 +590,7 @@ def run_b200(args):
             "parallelism": f"row bands of 4 rows, interleaved over {world} GPU(s); no collective in the data path",
             "family": family_used, "family_requested": args.family,
             "family_calibration_frames": CALIBRATION_FRAMES if family is None else 0,
-            "frame": frame_id,
+            "frame": frame_id, "cold_one_shot": cold,
             "e2e": e2e, "gpu_launches": launches_per_frame(family_used, args.max_depth) * K * world, "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_summary,
             "rays_per_frame": rays, "ms_per_frame": device_ms / K, "wall_ms_per_step_incl_flush": (t_wall1 - t_wall0) * 1e3 / K,
             "counters": stats,
@@ -514,6 +611,7 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--max-depth", type=int, default=6)
+    ap.add_argument("--no-cold", action="store_true", help="skip the cold one-shot probe (a fresh subprocess, N = 1 only)")
     ap.add_argument("--family", default="auto", choices=["auto", "persistent", "wavefront"],
                     help="kernel family; auto = the library measures both on the first frames and keeps the faster")
     args = ap.parse_args()

@@ -244,6 +244,12 @@ int rtgpu_context_render(rtgpu_context *context, const rtgpu_camera *camera, con
  * choice settled on; benchmarks report it). */
 int rtgpu_last_family(void);
 
+/* Records the wavefront family moved through HBM for the context's most recent host-buffer frame (zeros for a
+ * persistent-family frame): out[0] = hits queued over all levels (each written once and read once as a ray record),
+ * out[1] = node records (each written once, read once by the combine pass), out[2] / out[3] = bytes per ray / node
+ * record.  Benchmarks turn this into the frame's algorithmic queue traffic without a profiler. */
+int rtgpu_context_frame_records(rtgpu_context *context, uint64_t out[4]);
+
 /* -- pinned host memory ---------------------------------------------------------------------- */
 /* Page-locked, device-mapped host memory.  When out_rgb / out_rgb8 of a host-buffer render live in such
  * memory (these functions, cudaHostAlloc, cudaHostRegister, torch pin_memory ...) the persistent kernel writes

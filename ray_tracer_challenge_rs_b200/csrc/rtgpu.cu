@@ -641,6 +641,7 @@ struct rtgpu_context {
     struct HostStatus {
         unsigned long long counters[rt::NUM_COUNTERS];
         unsigned overflow, max_rays, n_nodes, valid;
+        unsigned long long queued_rays;  // hits queued over all levels of the frame (wavefront family)
     };
     HostStatus* h_status = nullptr;   // host view
     HostStatus* d_status = nullptr;   // device alias of the same memory
@@ -697,8 +698,13 @@ __global__ void publish_status_kernel(const unsigned long long* counters, const 
     if (threadIdx.x < rt::NUM_COUNTERS) out->counters[threadIdx.x] = counters ? counters[threadIdx.x] : 0ull;
     if (threadIdx.x == 0) {
         unsigned max_rays = 0;
+        unsigned long long queued = 0;
         if (wf)
-            for (int d = 0; d < 18; ++d) max_rays = max(max_rays, wf->n_rays[d] + wf->n_back[d]);
+            for (int d = 0; d < 18; ++d) {
+                max_rays = max(max_rays, wf->n_rays[d] + wf->n_back[d]);
+                queued += (unsigned long long)wf->n_rays[d] + wf->n_back[d];
+            }
+        out->queued_rays = queued;
         out->overflow = wf ? wf->overflow : 0u;
         out->max_rays = max_rays;
         out->n_nodes = wf ? wf->n_nodes : 0u;
@@ -1643,6 +1649,17 @@ int rtgpu_context_render_device(rtgpu_context* context, const rtgpu_camera* came
 }
 
 int rtgpu_last_family(void) { return g_last_family; }
+
+int rtgpu_context_frame_records(rtgpu_context* context, uint64_t out[4]) {
+    if (!context || !out) return fail(RTGPU_ERR_INVALID_ARGUMENT, "context or out is NULL");
+    if (!context->h_status || !context->h_status->valid) return fail(RTGPU_ERR_INVALID_ARGUMENT, "no host-buffer frame has been rendered on this context yet");
+    const bool f32 = context->d_reals32 != nullptr && context->wf_cap_rays && context->wf_bytes_rays / context->wf_cap_rays == sizeof(rt::WfRay<float>);
+    out[0] = context->h_status->queued_rays;
+    out[1] = context->h_status->n_nodes;
+    out[2] = f32 ? sizeof(rt::WfRay<float>) : sizeof(rt::WfRay<double>);
+    out[3] = f32 ? sizeof(rt::WfNode<float>) : sizeof(rt::WfNode<double>);
+    return RTGPU_OK;
+}
 
 int rtgpu_context_render(rtgpu_context* context, const rtgpu_camera* camera, const rtgpu_opts* opts, const rtgpu_rows* rows,
                          void* out_rgb, uint8_t* out_rgb8, rtgpu_stats* stats) {

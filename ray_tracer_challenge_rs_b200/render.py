@@ -175,6 +175,12 @@ class Renderer:
         abi.check(self._lib, st)
         return out_rgb, out_rgb8, dict(stats.as_dict(), family=last_family())
 
+    def frame_records(self) -> dict:
+        """What the wavefront family moved through HBM for the most recent host-buffer frame (``rtgpu_context_frame_records``)."""
+        out = (C.c_uint64 * 4)()
+        abi.check(self._lib, self._lib.rtgpu_context_frame_records(self._ctx, out))
+        return {"queued_rays": int(out[0]), "node_records": int(out[1]), "ray_record_bytes": int(out[2]), "node_record_bytes": int(out[3])}
+
     def render_device(
         self,
         camera: Camera,
