@@ -44,6 +44,9 @@ namespace rt {
 #ifndef RT_F32_OFFSET_ULPS
 #define RT_F32_OFFSET_ULPS 16  // f32 fast mode: over / under point offset in ulps of max(|point|, distance, 1); 8 .. 4096 swept in profiles/r2_notes.md
 #endif
+#ifndef RT_CANDIDATES
+#define RT_CANDIDATES 0  // 1: per-lane candidate masks, exact tests candidate by candidate (cover -1 %, every other scene +4..8 %: profiles/r2_notes.md)
+#endif
 #ifndef RT_LEAN_LOOP
 #define RT_LEAN_LOOP 1  // trace_unified: pointer-driven shape loop with a single branch per culled shape
 #endif
@@ -868,8 +871,8 @@ template <typename T>
 struct CullCursor<T, true> {  // tables in shared memory: shared-window byte addresses
     uint32_t at, end;
     template <typename SV>
-    RT_DEV CullCursor(const SV& sv, uint32_t n) {
-        at = (uint32_t)__cvta_generic_to_shared(sv.cull(0));
+    RT_DEV CullCursor(const SV& sv, uint32_t first, uint32_t n) {
+        at = (uint32_t)__cvta_generic_to_shared(sv.cull(first));
         end = at + n * (uint32_t)(CULL_REALS * sizeof(T));
         asm volatile("" : "+r"(end));  // opaque: a register, not eight uniform instructions per iteration to rebuild it
     }
@@ -889,8 +892,8 @@ template <typename T>
 struct CullCursor<T, false> {  // tables in global memory
     const T *at, *end;
     template <typename SV>
-    RT_DEV CullCursor(const SV& sv, uint32_t n) {
-        at = sv.cull(0);
+    RT_DEV CullCursor(const SV& sv, uint32_t first, uint32_t n) {
+        at = sv.cull(first);
         end = at + (size_t)n * CULL_REALS;
     }
     RT_DEV bool done() const { return at == end; }
@@ -915,20 +918,72 @@ struct CullCursor<T, false> {  // tables in global memory
 // SHADOW_EXIT: a lane whose shadow query has found a blocker leaves the loop.  Pays when whole warps are in
 // the same query (wavefront family: -8 % on cover); in the persistent kernel, where the lanes of a warp are in
 // different queries, the extra branch costs more than the idle lanes save.
+// The exact test of one shape of the uniform list (Ray::intersect, ray.rs:35-49 + the query's bookkeeping).
+template <typename T, bool FULL, bool SMEM>
+RT_DEV void exact_test(const SceneView<T, SMEM>& sv, uint32_t pos, const Ray<T>& ray, TraceAcc<T>& acc) {
+    const T* g = sv.shape(pos);
+    const int4 meta = sv.shape_meta(pos);
+    Ray<T> local;  // ray.rs:45-49
+    local.o = mat_point(g, ray.o);
+    local.d = mat_vector(g, ray.d);
+    T t0, t1, t2, t3;  // set by every local_intersect
+    int k = 0;
+    switch ((meta.z >> FLAG_TYPE_SHIFT) & 7) {
+    case 0: k = local_intersect<T, 0>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
+    case 1: k = local_intersect<T, 1>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
+    case 2: k = local_intersect<T, 2>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
+    case 3: if (FULL) k = local_intersect<T, 3>(local, g, meta.z, nullptr, t0, t1, t2, t3); else t0 = t1 = t2 = t3 = T(0); break;
+    case 4: if (FULL) k = local_intersect<T, 4>(local, g, meta.z, nullptr, t0, t1, t2, t3); else t0 = t1 = t2 = t3 = T(0); break;
+    default: if (FULL) k = local_intersect<T, 5>(local, g, meta.z, sv.triangle(pos), t0, t1, t2, t3); else t0 = t1 = t2 = t3 = T(0); break;
+    }
+    consume<T, 4>(acc, k, t0, t1, t2, t3, (int)pos, meta);
+}
+
 template <typename T, bool FULL, bool SHADOW_EXIT, bool SMEM>
 RT_DEV void trace_unified(const SceneView<T, SMEM>& sv, const Ray<T>& ray, TraceAcc<T>& acc) {
     const uint32_t n = sv.L.type_begin[NUM_SHAPE_TYPES];
-#if RT_CULL && RT_LEAN_LOOP
-    // The loop runs on the cull-record pointer alone: a culled shape (88 % of them on the cover frame) costs the
+#if RT_CULL && RT_CANDIDATES
+    // Two passes per block of 32 shapes.  (1) Every lane pre-tests ITS ray against the block, branch-free, and keeps
+    // the survivors as a bit mask.  (2) Each lane runs the exact tests of its own survivors, first survivor first:
+    // in round j every lane is on its j-th candidate, so the warp needs max-over-lanes(#survivors) rounds — 5-6 on
+    // the cover frame — where the single loop needed one round per shape that ANY lane's ray survives (12-15 at the
+    // deeper levels, each for a handful of lanes: local_intersect ran at 8 of 32 threads per instruction).  The
+    // price is per-lane table addresses in the exact test.
+    const T behind_below0 = acc.mode == MODE_CONTAINER ? -Real<T>::max() : T(0);
+    for (uint32_t base = 0; base < n; base += 32u) {
+        const uint32_t count = min(32u, n - base);
+        CullCursor<T, SMEM> cur(sv, base, count);
+        T behind_below = behind_below0;
+        keep_in_register(behind_below);
+        uint32_t mask = 0u, bit = 1u;
+        for (; !cur.done(); cur.next(), bit <<= 1) {
+            T cx, cy, cz, r2;
+            cur.load(cx, cy, cz, r2);
+            const T ocx = cx - ray.o.x, ocy = cy - ray.o.y, ocz = cz - ray.o.z;
+            const T bq = fma(ocz, ray.d.z, fma(ocy, ray.d.y, ocx * ray.d.x));
+            const T c2 = fma(ocz, ocz, fma(ocy, ocy, ocx * ocx));
+            const T ex = fma(c2, sv.cull_shrink(), -r2);
+            const bool outside = ex > T(0), behind = bq < behind_below, misses = ex * acc.dir_sq > bq * bq;
+            if (!(outside & (behind | misses))) mask |= bit;
+        }
+        while (mask) {
+            const uint32_t pos = base + (uint32_t)__ffs((int)mask) - 1u;
+            mask &= mask - 1u;
+            exact_test<T, FULL>(sv, pos, ray, acc);
+            // World::is_in_shadow (world.rs:106-111) is an `any`: a lane that has found a blocker is done
+            if (SHADOW_EXIT && acc.mode == MODE_SHADOW && acc.best_pos >= 0) mask = 0u;
+        }
+        if (SHADOW_EXIT && acc.mode == MODE_SHADOW && acc.best_pos >= 0) break;
+    }
+#elif RT_CULL && RT_LEAN_LOOP
+    // The loop runs on the cull-record cursor alone: a culled shape (88 % of them on the cover frame) costs the
     // pre-test, one add, one compare and one branch.  Everything else — the shape's position, the addresses of its
-    // geometry and meta records — is derived from the pointer on the rare path; the `asm` keeps the compiler from
+    // geometry and meta records — is derived from the cursor on the rare path; the `asm` keeps the compiler from
     // turning those addresses back into loop-carried counters (it emitted five adds per iteration).  The pre-test is
     // evaluated without short-circuits (one data-dependent branch instead of two), and a shadow query that has found
-    // its blocker leaves by moving the pointer to the last record instead of a `break` (no per-iteration
+    // its blocker leaves by moving the cursor to the last record instead of a `break` (no per-iteration
     // BSSY / BSYNC pair around the body).
-    // shared-memory tables: a 32-bit shared-window address and ld.shared, so that the loop carries two registers
-    // (ptxas otherwise rebuilds the window base from SR_CgaCtaId in every iteration); global tables: a pointer
-    CullCursor<T, SMEM> cur(sv, n);
+    CullCursor<T, SMEM> cur(sv, 0u, n);
     // "the centre is behind the origin" only culls when negative distances are of no interest (everything but the
     // container walk): comparing against -max instead of 0 switches it off without a mode test in the loop
     T behind_below = acc.mode == MODE_CONTAINER ? -Real<T>::max() : T(0);
@@ -944,6 +999,10 @@ RT_DEV void trace_unified(const SceneView<T, SMEM>& sv, const Ray<T>& ray, Trace
         if (outside & (behind | misses)) continue;
         uint32_t pos = cur.position(n);
         asm volatile("" : "+r"(pos));
+        exact_test<T, FULL>(sv, pos, ray, acc);
+        // World::is_in_shadow (world.rs:106-111) is an `any`: a lane that has found a blocker is done
+        if (SHADOW_EXIT && acc.mode == MODE_SHADOW && acc.best_pos >= 0) cur.finish();
+    }
 #else
     for (uint32_t pos = 0; pos < n; ++pos) {
 #if RT_CULL
@@ -957,30 +1016,10 @@ RT_DEV void trace_unified(const SceneView<T, SMEM>& sv, const Ray<T>& ray, Trace
             if (ex > T(0) && ((acc.mode != MODE_CONTAINER && bq < T(0)) || ex * acc.dir_sq > bq * bq)) continue;
         }
 #endif
-#endif
-        const T* g = sv.shape(pos);
-        const int4 meta = sv.shape_meta(pos);
-        Ray<T> local;  // ray.rs:45-49
-        local.o = mat_point(g, ray.o);
-        local.d = mat_vector(g, ray.d);
-        T t0, t1, t2, t3;  // set by every local_intersect
-        int k = 0;
-        switch ((meta.z >> FLAG_TYPE_SHIFT) & 7) {
-        case 0: k = local_intersect<T, 0>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
-        case 1: k = local_intersect<T, 1>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
-        case 2: k = local_intersect<T, 2>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
-        case 3: if (FULL) k = local_intersect<T, 3>(local, g, meta.z, nullptr, t0, t1, t2, t3); else t0 = t1 = t2 = t3 = T(0); break;
-        case 4: if (FULL) k = local_intersect<T, 4>(local, g, meta.z, nullptr, t0, t1, t2, t3); else t0 = t1 = t2 = t3 = T(0); break;
-        default: if (FULL) k = local_intersect<T, 5>(local, g, meta.z, sv.triangle(pos), t0, t1, t2, t3); else t0 = t1 = t2 = t3 = T(0); break;
-        }
-        consume<T, 4>(acc, k, t0, t1, t2, t3, (int)pos, meta);
-        // World::is_in_shadow (world.rs:106-111) is an `any`: a lane that has found a blocker is done
-#if RT_CULL && RT_LEAN_LOOP
-        if (SHADOW_EXIT && acc.mode == MODE_SHADOW && acc.best_pos >= 0) cur.finish();
-#else
+        exact_test<T, FULL>(sv, pos, ray, acc);
         if (SHADOW_EXIT && acc.mode == MODE_SHADOW && acc.best_pos >= 0) break;
-#endif
     }
+#endif
 }
 
 // ---- pair-list trace: World::collect_intersections for the 32 rays of a warp at once --------------------------
