@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Markdown summary of profiles/r1_wavefront_launches.csv (the output of wf_launches.sh).
+"""Markdown summary of a per-launch capture (the output of wf_launches.sh).
 
-    python profiles/tools/wf_table.py <bench ms/frame> > profiles/r1_wavefront_launches.md
+    python profiles/tools/wf_table.py <bench ms/frame> [csv under profiles/] [title] > profiles/rN_wavefront_launches.md
 """
 import collections
 import csv
@@ -10,7 +10,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 bench_ms = sys.argv[1] if len(sys.argv) > 1 else "?"
-rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", "r1_wavefront_launches.csv"))) if len(r) > 10]
+csv_name = sys.argv[2] if len(sys.argv) > 2 else "r1_wavefront_launches.csv"
+title = sys.argv[3] if len(sys.argv) > 3 else "cover@1920x1080 f64"
+rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", csv_name))) if len(r) > 10]
 per = collections.OrderedDict()
 for r in rows[1:]:
     per.setdefault(r[0], {"name": r[4]})[r[-3]] = r[-1]
@@ -28,7 +30,7 @@ def short(n):
 
 
 tot = sum(f(v, "gpu__time_duration.sum") for v in per.values())
-print("# Wavefront family: the %d launches of one cover@1920x1080 f64 frame (ncu, --clock-control none)\n" % len(per))
+print("# Wavefront family: the %d launches of one %s frame (ncu, --clock-control none; `profiles/%s`)\n" % (len(per), title, csv_name))
 print("Command: `profiles/tools/wf_launches.sh` (bench.py --family wavefront --steps 2 --warmup 3 exited 0 first; the capture is")
 print("the last timed frame).  Times under ncu are serialised and cold-cache: use the shares, not the absolutes")
 print("(bench.py measures %s ms for the frame with CUDA events; the launches below sum to %.2f ms).\n" % (bench_ms, tot / 1e6))
@@ -48,19 +50,22 @@ share = lambda sub: 100 * sum(f(v, "gpu__time_duration.sum") for v in per.values
 print("\nLevel kernels: %.1f %% of the frame; combine kernels %.1f %%; counter commit %.1f %%." % (share("wf_level"), share("combine"), share("commit")))
 print("DRAM per frame: %.0f MB written, %.0f MB read (bench.py reports the sum as `roofline.traffic`)." % (
     sum(f(v, "dram__bytes_write.sum") for v in per.values()) / 1e6, sum(f(v, "dram__bytes_read.sum") for v in per.values()) / 1e6))
-print("""
+reading = {
+    "r1_wavefront_launches.csv": """
 Reading: the level kernels are issue-bound on fixed-latency FP64 dependencies (`wait` ~2.5 cycles per issue with 3.9
 warps per scheduler), FP64 pipe 33-38 % busy, instruction caches healthy on this scene (icc 97 %, GPC cache 30-56 %).
-Instruction mix of the level-0 launch (ncu source view): DMUL + DFMA + DADD + DSETP 33 % of the warp instructions,
-integer / move / address arithmetic 30 %, branches and convergence barriers 12 %, LDS 6 %.
-On pattern-heavy scenes (table, metal) the same kernels run at icc 87-93 % / GPC cache 83-92 % and are instruction-supply bound.
-The combine kernels move one 120-byte node record per interior node at ~3.8 TB/s; they are latency-bound at 5 % issue
-(4x more CTAs changed nothing: 2.441 vs 2.445 ms).
-
-`r1_final_launches.csv`: the `--metrics gpu__time_duration.sum` launch list of the default `python bench.py --steps 2 --warmup 3`.
-Caveat: under ncu every launch is serialised and pays the profiler's per-launch overhead, so the family calibration —
-which times whole frames — can see the multi-launch wavefront frame as slower and settle on the persistent kernel
-there.  Outside the profiler the same command settles on the wavefront family (bench line: `config.family`), which is
-what the table above profiles.
-`r1d_wf_level_kernel_metrics.csv`: `ncu --set full` of the level-0 and level-1 launches (raw page; captured before the
-last three micro-optimisations, 2.53 ms per frame at the time).""")
+The combine kernels move one node record per interior node at ~3.8 TB/s; they are latency-bound at 5 % issue.""",
+    "r2b_wavefront_launches.csv": """
+Reading (round 2; the capture window starts at level 1 of one frame and ends with level 0 of the next: launch 14 is a
+level-0 launch): with the node state parked in shared memory the level kernels run at 80 registers, 6 CTAs per SM
+(5.9 warps per scheduler instead of 3.9): **issue slots 67-70 % busy (round 1: 54-57 %), FP64 pipe 47-52 % (33-40 %)**;
+instruction counts and threads per instruction are those of round 1 — the divergence of the exact tests at depth
+(17.6-25 threads per instruction at levels 1-6) is unchanged and is what is left.  The combine kernels (9.6 % of the
+frame) are memory-latency bound at ~3.8 TB/s.""",
+    "r2_synthetic_1e5_8k_launches.csv": """
+Reading: the BVH path.  Level 0 is 70 % of the frame at 18.7 threads per instruction; the deeper levels run at 6-9.
+After moving the box tests to single precision the FP64 pipe is 2-4 % busy (only the exact leaf tests use it) and the
+kernels are bound by issue slots spent on partially filled warps, not by memory: DRAM carries 1.5 GB in the 49 ms of
+level 0 (31 GB/s, 0.5 % of the HBM peak), L2 serves the 20 MB of nodes and shapes.""",
+}
+print(reading.get(csv_name, ""))
