@@ -1218,6 +1218,13 @@ RT_COLD V3<T> pattern_color_at(const SceneView<T, SMEM>& sv, int pattern, V3<T> 
 // ---------------------------------------------------------------------------------------------
 // The pieces of a node both kernel families (and the known-answer probes of rt_probe.cuh) are built from.
 
+// Image row of the k-th row a launch renders (rt_scene.h CameraParams)
+template <typename T>
+RT_DEV uint32_t image_row(const CameraParams<T>& cam, uint32_t k) {
+    const uint32_t q = k / cam.band_rows;
+    return ((q / cam.band_take) * cam.shard_count + cam.shard_index + q % cam.band_take) * cam.band_rows + k % cam.band_rows;
+}
+
 // Camera::ray_for_pixel, camera.rs:52-68 (x, y: image column and row)
 template <typename T>
 RT_DEV Ray<T> camera_ray(const CameraParams<T>& cam, uint32_t x, uint32_t y) {
@@ -1434,7 +1441,7 @@ render_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, Sce
                         uint32_t k = tile_row * TILE_H + in / TILE_W;
                         state = ST_FETCH;  // padding slot: try again on the next round
                         if (x < cam.hsize && k < cam.n_rows) {
-                            uint32_t y = ((k / cam.band_rows) * cam.shard_count + cam.shard_index) * cam.band_rows + k % cam.band_rows;
+                            uint32_t y = image_row(cam, k);
                             ray = camera_ray(cam, x, y);
                             if (cam.probe_ray) ray.d = mk<T>(cam.inv[0], cam.inv[1], cam.inv[2]);
                             out_index = (size_t)(cam.out_full_frame ? y : k) * cam.hsize + x;

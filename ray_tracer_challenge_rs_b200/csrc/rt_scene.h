@@ -113,9 +113,12 @@ struct CameraParams {
     T inv[12];
     T origin[3];
     uint32_t hsize, vsize;
-    // rows: compact row k of this launch is image row ((k / band_rows) * shard_count + shard_index) * band_rows + k % band_rows
+    // rows: with q = k / band_rows the compact row k of this launch is image row
+    //   ((q / band_take) * shard_count + shard_index + q % band_take) * band_rows + k % band_rows
+    // i.e. out of every `shard_count` consecutive bands the launch renders `band_take` of them, starting at band
+    // `shard_index` (band_take = 1: the public rtgpu_rows selection; > 1: the unequal parts of a chunked host render)
     uint32_t n_rows;  // rows rendered by this launch
-    uint32_t band_rows, shard_index, shard_count;
+    uint32_t band_rows, shard_index, shard_count, band_take;
     uint32_t max_depth;  // World::MAX_REFLECTION_ITERATIONS (world.rs:15)
     uint32_t tile_stride;  // coprime to the number of 8x4 tiles: scattered tile order (rt_kernel.cuh)
     uint32_t out_full_frame;  // 1: outputs are full-frame buffers indexed by image row (zero-copy into the

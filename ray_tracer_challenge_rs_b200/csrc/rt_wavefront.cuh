@@ -216,7 +216,7 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                 const uint32_t k = (tile / tiles_x) * TILE_H + in / TILE_W;
                 active = x < cam.hsize && k < cam.n_rows;
                 if (active) {
-                    const uint32_t y = ((k / cam.band_rows) * cam.shard_count + cam.shard_index) * cam.band_rows + k % cam.band_rows;
+                    const uint32_t y = image_row(cam, k);
                     const Ray<T> cr = camera_ray(cam, x, y);
                     const V3<T> origin = cr.o, d = cam.probe_ray ? mk<T>(cam.inv[0], cam.inv[1], cam.inv[2]) : cr.d;
                     PK(PK_P + 0) = origin.x; PK(PK_P + 1) = origin.y; PK(PK_P + 2) = origin.z;

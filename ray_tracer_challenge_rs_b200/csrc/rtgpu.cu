@@ -555,6 +555,7 @@ uint64_t scene_input_hash(const rtgpu_scene* s) {
 
 struct RowSel {
     uint32_t band_rows, shard_index, shard_count;
+    uint32_t take = 1;  // bands rendered out of every shard_count, starting at band shard_index (public selections: 1)
 };
 
 int normalise_rows(const rtgpu_rows* rows, uint32_t vsize, RowSel* out) {
@@ -573,15 +574,24 @@ int normalise_rows(const rtgpu_rows* rows, uint32_t vsize, RowSel* out) {
 }
 
 uint32_t count_rows(const RowSel& r, uint32_t vsize) {
-    const uint64_t period = (uint64_t)r.band_rows * r.shard_count;
-    if (period == 0) return 0;
-    // full periods, then the tail
-    const uint64_t full = vsize / period;
-    uint64_t n = full * r.band_rows;
-    const uint64_t rem = vsize - full * period;
-    const uint64_t lo = (uint64_t)r.shard_index * r.band_rows;
-    if (rem > lo) n += std::min<uint64_t>(r.band_rows, rem - lo);
+    if (r.band_rows == 0 || r.shard_count == 0) return 0;
+    // bands b with (b % shard_count) in [shard_index, shard_index + take); the last band of the image may be partial
+    auto selected_among_first = [&r](uint64_t n_bands) {
+        const uint64_t part = n_bands % r.shard_count;
+        const uint64_t in_part = part > r.shard_index ? std::min<uint64_t>(part - r.shard_index, r.take) : 0;
+        return (n_bands / r.shard_count) * r.take + in_part;
+    };
+    const uint64_t full_bands = vsize / r.band_rows, rem_rows = vsize % r.band_rows;
+    uint64_t n = selected_among_first(full_bands) * r.band_rows;
+    const uint64_t last = full_bands % r.shard_count;  // position of the partial band inside its period
+    if (rem_rows && last >= r.shard_index && last < (uint64_t)r.shard_index + r.take) n += rem_rows;
     return (uint32_t)n;
+}
+
+// image row of the k-th selected row (the kernels' image_row)
+uint32_t selected_row(const RowSel& r, uint32_t k) {
+    const uint32_t q = k / r.band_rows;
+    return ((q / r.take) * r.shard_count + r.shard_index + q % r.take) * r.band_rows + k % r.band_rows;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1000,6 +1010,7 @@ void fill_camera(const rtgpu_camera* c, const RowSel& rows, uint32_t n_rows, uin
     out->band_rows = rows.band_rows;
     out->shard_index = rows.shard_index;
     out->shard_count = rows.shard_count;
+    out->band_take = rows.take;
     out->max_depth = max_depth;
     // stride for the scattered tile order: near the golden ratio of the tile count, made coprime to it
     const uint64_t n_tiles = (uint64_t)((c->hsize + rt::TILE_W - 1) / rt::TILE_W) * ((n_rows + rt::TILE_H - 1) / rt::TILE_H);
@@ -1058,15 +1069,19 @@ int render_wavefront(rtgpu_context* ctx, const T* d_reals, const rt::CameraParam
 
 int render_device_impl(rtgpu_context* ctx, const rtgpu_camera* camera, const rtgpu_opts* opts, const rtgpu_rows* rows,
                        void* d_out_rgb, uint8_t* d_out_rgb8, uint64_t* d_counters, cudaStream_t stream, uint32_t* out_n_rows,
-                       int family, bool full_frame_out = false, bool wavefront_blocking = true) {
+                       int family, bool full_frame_out = false, bool wavefront_blocking = true, const RowSel* internal_sel = nullptr) {
     if (!ctx || !camera) return fail(RTGPU_ERR_INVALID_ARGUMENT, "context or camera is NULL");
     if (!d_out_rgb && !d_out_rgb8) return fail(RTGPU_ERR_INVALID_ARGUMENT, "both output pointers are NULL");
     uint32_t precision, max_depth;
     int st = check_opts(opts, &precision, &max_depth);
     if (st != RTGPU_OK) return st;
     RowSel sel;
-    st = normalise_rows(rows, camera->vsize, &sel);
-    if (st != RTGPU_OK) return st;
+    if (internal_sel) {
+        sel = *internal_sel;
+    } else {
+        st = normalise_rows(rows, camera->vsize, &sel);
+        if (st != RTGPU_OK) return st;
+    }
     const uint32_t n_rows = count_rows(sel, camera->vsize);
     if (out_n_rows) *out_n_rows = n_rows;
     if (n_rows == 0 || camera->hsize == 0) return RTGPU_OK;  // nothing to render
@@ -1280,12 +1295,14 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
         if (trial) tune_end(ctx, ctx->stream, key, family);
         return RTGPU_OK;
     }
-    // Wavefront family, whole frame: render it as two interleaved halves (16-row bands, like two devices would) and
-    // copy the first half while the second one renders — the queues are reused, and the 1 ms copy of a 1080p f64
-    // frame is half hidden.  RTGPU_E2E_CHUNKS=1 disables.
+    // Wavefront family, whole frame: render it in two interleaved parts (16-row bands) and copy the first part while
+    // the second one renders; the queues are reused.  The parts are UNEQUAL: with T(f) ~ 0.25 + 1.62 f ms for a
+    // fraction f of the 1080p cover frame and 0.94 f ms for its copy, the first part should be as large as the
+    // second part's kernels can still hide its copy (f ~ 0.7): 3 of every 4 bands, then the fourth — 2.60 -> 2.42 ms
+    // end to end against equal halves.  RTGPU_E2E_SPLIT=<take>/<period> overrides, RTGPU_E2E_CHUNKS=1 disables.
     const char* chunks_env = getenv("RTGPU_E2E_CHUNKS");
     // Only for pinned host buffers: a device-to-host copy into pageable memory blocks the submitting thread, so the
-    // second half's kernels would not even be enqueued before the first half's copy has finished.
+    // second part's kernels would not even be enqueued before the first part's copy has finished.
     const bool pinned = (!out_rgb || map_rgb) && (!out_rgb8 || map_rgb8);
     const bool chunked = family == FAMILY_WAVEFRONT && pinned && sel.shard_count == 1 && sel.band_rows >= camera->vsize && camera->vsize >= 64 &&
                          (uint64_t)camera->hsize * camera->vsize >= (1u << 18) && !(chunks_env && chunks_env[0] == '1');
@@ -1295,25 +1312,27 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
             CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_chunk, cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
         }
-        constexpr uint32_t BAND = 16;
-        uint32_t CHUNKS = 2;
-        if (chunks_env && chunks_env[0] >= '2' && chunks_env[0] <= '8') CHUNKS = (uint32_t)(chunks_env[0] - '0');
+        constexpr uint32_t BAND = 16, CHUNKS = 2;
+        uint32_t take0 = 3, period = 4;  // 1/2 2.60, 3/5 2.50, 2/3 2.46, 7/10 2.42, 3/4 2.42, 4/5 2.45 ms (cover@1080p)
+        if (const char* sp = getenv("RTGPU_E2E_SPLIT"); sp && *sp) {
+            unsigned a = 0, b = 0;
+            if (sscanf(sp, "%u/%u", &a, &b) == 2 && a >= 1 && b >= 2 && a < b && b <= 64) {
+                take0 = a;
+                period = b;
+            }
+        }
         size_t rows_before = 0;
         for (uint32_t c = 0; c < CHUNKS; ++c) {
-            rtgpu_rows sub;
-            sub.band_rows = BAND;
-            sub.shard_index = c;
-            sub.shard_count = CHUNKS;
-            RowSel sub_sel{BAND, c, CHUNKS};
+            RowSel sub_sel{BAND, c == 0 ? 0u : take0, period, c == 0 ? take0 : period - take0};
             const uint32_t rows_c = count_rows(sub_sel, camera->vsize);
             char* d_rgb_c = out_rgb ? (char*)ctx->d_out + rows_before * row_rgb : nullptr;
             uint8_t* d_rgb8_c = out_rgb8 ? ctx->d_out8 + rows_before * row_rgb8 : nullptr;
             ctx->wf_keep_overflow = c > 0;
-            st = render_device_impl(ctx, camera, opts, &sub, d_rgb_c, d_rgb8_c, reinterpret_cast<uint64_t*>(ctx->d_counters), ctx->stream, nullptr,
-                                    family, false, /*wavefront_blocking=*/false);
+            st = render_device_impl(ctx, camera, opts, nullptr, d_rgb_c, d_rgb8_c, reinterpret_cast<uint64_t*>(ctx->d_counters), ctx->stream, nullptr,
+                                    family, false, /*wavefront_blocking=*/false, &sub_sel);
             ctx->wf_keep_overflow = false;
             if (st != RTGPU_OK) return st;
-            // the last chunk's copies follow its kernels on the main stream; earlier ones go to the copy stream
+            // the last part's copies follow its kernels on the main stream; earlier ones go to the copy stream
             cudaStream_t cs = ctx->stream;
             if (c + 1 < CHUNKS) {
                 CUDA_TRY(cudaEventRecord(ctx->ev_chunk, ctx->stream));
@@ -1323,24 +1342,26 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
                 CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
                 if ((st = publish_status(ctx)) != RTGPU_OK) return st;
             }
-            // compact band b of this chunk -> image rows of band (b * CHUNKS + c): one strided copy + the partial last band
-            const uint32_t full_bands = rows_c / BAND, tail_rows = rows_c % BAND;
-            const size_t first_row = (size_t)c * BAND;
+            // every period contributes `take` consecutive bands, contiguous in the compact buffer AND in the image: one
+            // strided copy for the complete groups, one plain copy for what is left of the last group
+            const uint32_t group_rows = sub_sel.take * BAND;
+            const uint32_t full_groups = rows_c / group_rows, tail_rows = rows_c % group_rows;
+            const size_t first_row = (size_t)sub_sel.shard_index * BAND, period_rows = (size_t)period * BAND;
             if (out_rgb) {
-                if (full_bands)
-                    CUDA_TRY(cudaMemcpy2DAsync((char*)out_rgb + first_row * row_rgb, (size_t)CHUNKS * BAND * row_rgb, d_rgb_c, (size_t)BAND * row_rgb,
-                                               (size_t)BAND * row_rgb, full_bands, cudaMemcpyDeviceToHost, cs));
+                if (full_groups)
+                    CUDA_TRY(cudaMemcpy2DAsync((char*)out_rgb + first_row * row_rgb, period_rows * row_rgb, d_rgb_c, (size_t)group_rows * row_rgb,
+                                               (size_t)group_rows * row_rgb, full_groups, cudaMemcpyDeviceToHost, cs));
                 if (tail_rows)
-                    CUDA_TRY(cudaMemcpyAsync((char*)out_rgb + (first_row + (size_t)full_bands * CHUNKS * BAND) * row_rgb,
-                                             d_rgb_c + (size_t)full_bands * BAND * row_rgb, (size_t)tail_rows * row_rgb, cudaMemcpyDeviceToHost, cs));
+                    CUDA_TRY(cudaMemcpyAsync((char*)out_rgb + (first_row + (size_t)full_groups * period_rows) * row_rgb,
+                                             d_rgb_c + (size_t)full_groups * group_rows * row_rgb, (size_t)tail_rows * row_rgb, cudaMemcpyDeviceToHost, cs));
             }
             if (out_rgb8) {
-                if (full_bands)
-                    CUDA_TRY(cudaMemcpy2DAsync(out_rgb8 + first_row * row_rgb8, (size_t)CHUNKS * BAND * row_rgb8, d_rgb8_c, (size_t)BAND * row_rgb8,
-                                               (size_t)BAND * row_rgb8, full_bands, cudaMemcpyDeviceToHost, cs));
+                if (full_groups)
+                    CUDA_TRY(cudaMemcpy2DAsync(out_rgb8 + first_row * row_rgb8, period_rows * row_rgb8, d_rgb8_c, (size_t)group_rows * row_rgb8,
+                                               (size_t)group_rows * row_rgb8, full_groups, cudaMemcpyDeviceToHost, cs));
                 if (tail_rows)
-                    CUDA_TRY(cudaMemcpyAsync(out_rgb8 + (first_row + (size_t)full_bands * CHUNKS * BAND) * row_rgb8,
-                                             d_rgb8_c + (size_t)full_bands * BAND * row_rgb8, (size_t)tail_rows * row_rgb8, cudaMemcpyDeviceToHost, cs));
+                    CUDA_TRY(cudaMemcpyAsync(out_rgb8 + (first_row + (size_t)full_groups * period_rows) * row_rgb8,
+                                             d_rgb8_c + (size_t)full_groups * group_rows * row_rgb8, (size_t)tail_rows * row_rgb8, cudaMemcpyDeviceToHost, cs));
             }
             if (c + 1 < CHUNKS) CUDA_TRY(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
             rows_before += rows_c;
@@ -1357,7 +1378,7 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
     // compact band b (rows [b*band_rows, ...)) of this shard -> image rows of band (b*shard_count + shard_index)
     for (uint32_t k = 0; k < n_rows; k += sel.band_rows) {
         const uint32_t rows_here = std::min(sel.band_rows, n_rows - k);
-        const uint32_t y = ((k / sel.band_rows) * sel.shard_count + sel.shard_index) * sel.band_rows;
+        const uint32_t y = selected_row(sel, k);
         if (out_rgb)
             CUDA_TRY(cudaMemcpyAsync((char*)out_rgb + (size_t)y * row_rgb, (char*)ctx->d_out + (size_t)k * row_rgb,
                                      row_rgb * rows_here, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1598,7 +1619,7 @@ uint32_t rtgpu_rows_list(const rtgpu_rows* rows, uint32_t vsize, uint32_t* out_r
     const uint32_t n = count_rows(sel, vsize);
     if (out_rows)
         for (uint32_t k = 0; k < n && k < capacity; ++k)
-            out_rows[k] = ((k / sel.band_rows) * sel.shard_count + sel.shard_index) * sel.band_rows + k % sel.band_rows;
+            out_rows[k] = selected_row(sel, k);
     return n;
 }
 
@@ -1804,7 +1825,7 @@ int rtgpu_debug_color_at(rtgpu_context* context, const double origin[3], const d
     rt::CameraParams<double> cam;
     memset(&cam, 0, sizeof(cam));
     cam.hsize = cam.vsize = cam.n_rows = cam.band_rows = 1u;
-    cam.shard_count = 1u;
+    cam.shard_count = cam.band_take = 1u;
     cam.max_depth = max_depth;
     cam.tile_stride = 0u;
     cam.probe_ray = 1u;

@@ -505,6 +505,28 @@ def test_auto_family_survives_without_room_for_the_queues(monkeypatch):
     assert [st["family"] for _, _, st in frames[1:]] == ["persistent"] * 3
 
 
+@pytest.mark.parametrize("split", [None, "1/2", "2/3", "5/8", "7/8"])
+@pytest.mark.parametrize("height", [300, 257, 64 * 5 + 1])
+def test_wavefront_chunked_host_render_unequal_parts(split, height, monkeypatch):
+    """The chunked host render takes `take` of every `period` 16-row bands first and the rest second (unequal parts:
+    the second part's kernels hide the first part's copy): every split, ragged heights included, is the frame."""
+    from ray_tracer_challenge_rs_b200.render import PinnedArray
+
+    if split:
+        monkeypatch.setenv("RTGPU_E2E_SPLIT", split)
+    flat, camera = load_scene_fixture("cover")
+    cam = camera.resized(1024, height)
+    with Renderer(flat) as r:
+        want, want8, wstats = r.render(cam, family="persistent")
+        pin, pin8 = PinnedArray((1024 * height, 3)), PinnedArray((1024 * height, 3), np.uint8)
+        pin.array[:] = -1.0
+        _, _, st = r.render(cam, family="wavefront", out_rgb=pin.array, out_rgb8=pin8.array)
+        assert np.array_equal(pin.array.view(np.uint64), want.view(np.uint64)) and np.array_equal(pin8.array, want8)
+        assert {k: st[k] for k in COUNTERS} == {k: wstats[k] for k in COUNTERS}
+        pin.close()
+        pin8.close()
+
+
 def test_wavefront_chunked_host_render_overflows_and_recovers(monkeypatch):
     """Host-buffer renders of the wavefront family into PINNED memory run as two interleaved halves whose copies
     overlap; with a tiny first guess for the queues both halves overflow, the buffers grow, the frame is rendered
