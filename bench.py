@@ -412,7 +412,7 @@ def run_b200(args):
                                max_depth=args.max_depth, rows=rows, family=family)
 
     # ---- device-resident timing ("value") ----
-    # family "auto": the library times its first two frames of each kernel family (P, W, P, W) and keeps the
+    # family "auto": the library times its first two frames of each kernel family (W, P, W, P) and keeps the
     # faster; those calibration frames come before the warm-up so that warm-up and timed steps run the settled one
     for _ in range(CALIBRATION_FRAMES if family is None else 0):
         launch()

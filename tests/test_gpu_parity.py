@@ -528,7 +528,7 @@ def test_wavefront_chunked_host_render_unequal_parts(split, height, monkeypatch)
 
 
 def test_wavefront_chunked_host_render_overflows_and_recovers(monkeypatch):
-    """Host-buffer renders of the wavefront family into PINNED memory run as two interleaved halves whose copies
+    """Host-buffer renders of the wavefront family into PINNED memory run as two interleaved parts whose copies
     overlap; with a tiny first guess for the queues both halves overflow, the buffers grow, the frame is rendered
     again — same bits as the persistent kernel.  Pageable buffers take the single-sequence path."""
     from ray_tracer_challenge_rs_b200.render import PinnedArray
