@@ -49,11 +49,9 @@ struct WfRay {
 };
 
 template <typename T>
-struct WfNode {
-    int parent;       // parent node, or -1 for a level-0 node
-    int slot;         // slot in the parent (0 reflected, 1 refracted); level 0: unused
-    unsigned pixel;   // level 0: output index of the pixel
-    int flags;        // FR_SCHLICK
+struct alignas(32) WfNode {  // f64: 96 bytes = three 32-byte sectors exactly (104 unaligned bytes cost the combine pass 1.9x its payload in DRAM reads)
+    int link;         // >= 0: the parent node; < 0: a level-0 node, ~link is the output index of its pixel
+    int slot_flags;   // bit 0: slot in the parent (0 reflected, 1 refracted); bit 1: Schlick blend (world.rs:59)
     T k_parent;       // scale applied to this node's colour when it is handed to the parent (world.rs:127,156)
     T reflectance;
     T surface[3];
@@ -442,10 +440,8 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                     flags &= ~(FR_REFLECT | FR_REFRACT);  // no record, no children: the frame is re-rendered anyway
                 } else if (interior) {
                     WfNode<T> nd;
-                    nd.parent = parent;
-                    nd.slot = slot;
-                    nd.pixel = out_index;
-                    nd.flags = flags & FR_SCHLICK;
+                    nd.link = parent >= 0 ? parent : ~(int)out_index;
+                    nd.slot_flags = slot | ((flags & FR_SCHLICK) ? 2 : 0);
                     nd.k_parent = k_parent;
                     nd.reflectance = (flags & FR_SCHLICK) ? PK(PK_REFLECTANCE) : T(0);
                     nd.surface[0] = surface.x; nd.surface[1] = surface.y; nd.surface[2] = surface.z;
@@ -510,26 +506,54 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
     }
 }
 
-// World::shade_hit's tail (world.rs:59-66) for the nodes of one level, deepest level first.
+// World::shade_hit's tail (world.rs:59-66) for the nodes of one level, deepest level first.  Memory-latency bound: a
+// thread fetches its whole record with 128-bit loads (six per f64 record, all in flight before the first use) and
+// handles two records per iteration.
+template <typename T>
+RT_DEV WfNode<T> wf_load_node(const WfNode<T>* p) {
+    static_assert(sizeof(WfNode<T>) % 16 == 0, "node records are read with 128-bit loads");
+    union {
+        uint4 raw[sizeof(WfNode<T>) / 16];
+        WfNode<T> node;
+    } u;
+    const uint4* src = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (unsigned k = 0; k < sizeof(WfNode<T>) / 16; ++k) u.raw[k] = src[k];
+    return u.node;
+}
+
+template <typename T>
+RT_DEV void wf_combine_node(WfNode<T>* __restrict__ nodes, const WfNode<T>& n, T* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8) {
+    const V3<T> surface = mk<T>(n.surface[0], n.surface[1], n.surface[2]);
+    const V3<T> reflected = mk<T>(n.reflected[0], n.reflected[1], n.reflected[2]);
+    const V3<T> refracted = mk<T>(n.refracted[0], n.refracted[1], n.refracted[2]);
+    V3<T> colour;
+    if (n.slot_flags & 2) colour = (surface + (reflected * n.reflectance)) + (refracted * (T(1) - n.reflectance));
+    else colour = (surface + reflected) + refracted;
+    if (n.link < 0) {
+        wf_store_pixel(out_rgb, out_rgb8, (size_t)(unsigned)~n.link, colour);  // Camera::render_parallel, camera.rs:108
+    } else {
+        const V3<T> c = colour * n.k_parent;  // world.rs:127 / 156
+        T* dst = (n.slot_flags & 1) == 0 ? nodes[n.link].reflected : nodes[n.link].refracted;
+        dst[0] = c.x; dst[1] = c.y; dst[2] = c.z;
+    }
+}
+
 template <typename T>
 __global__ void wf_combine_kernel(WfNode<T>* __restrict__ nodes, const WfCounts* __restrict__ counts, int level, unsigned cap_nodes,
                                   T* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8) {
     const unsigned begin = level == 0 ? 0u : min(counts->node_end[level - 1], cap_nodes);
     const unsigned end = min(counts->node_end[level], cap_nodes);
-    for (unsigned i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
-        const WfNode<T>& n = nodes[i];
-        const V3<T> surface = mk<T>(n.surface[0], n.surface[1], n.surface[2]);
-        const V3<T> reflected = mk<T>(n.reflected[0], n.reflected[1], n.reflected[2]);
-        const V3<T> refracted = mk<T>(n.refracted[0], n.refracted[1], n.refracted[2]);
-        V3<T> colour;
-        if (n.flags & FR_SCHLICK) colour = (surface + (reflected * n.reflectance)) + (refracted * (T(1) - n.reflectance));
-        else colour = (surface + reflected) + refracted;
-        if (n.parent < 0) {
-            wf_store_pixel(out_rgb, out_rgb8, (size_t)n.pixel, colour);  // Camera::render_parallel, camera.rs:108
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += 2u * stride) {
+        const unsigned j = i + stride;
+        const WfNode<T> a = wf_load_node(nodes + i);
+        if (j < end) {
+            const WfNode<T> b2 = wf_load_node(nodes + j);
+            wf_combine_node(nodes, a, out_rgb, out_rgb8);
+            wf_combine_node(nodes, b2, out_rgb, out_rgb8);
         } else {
-            const V3<T> c = colour * n.k_parent;  // world.rs:127 / 156
-            T* dst = n.slot == 0 ? nodes[n.parent].reflected : nodes[n.parent].refracted;
-            dst[0] = c.x; dst[1] = c.y; dst[2] = c.z;
+            wf_combine_node(nodes, a, out_rgb, out_rgb8);
         }
     }
 }

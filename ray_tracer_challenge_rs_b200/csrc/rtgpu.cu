@@ -895,6 +895,10 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, level_kernel, RT_WF_THREADS, smem));
     if (blocks_per_sm < 1) return fail(RTGPU_ERR_CUDA, "wavefront kernel does not fit on an SM (smem %zu B)", smem);
     const uint64_t pixels = (uint64_t)cam.hsize * cam.n_rows;
+    // node records address their pixel with 31 bits (rt_wavefront.cuh WfNode::link); reported like a buffer that cannot
+    // be had, so that automatic mode renders such a frame with the persistent kernel
+    if ((uint64_t)cam.hsize * (cam.out_full_frame ? cam.vsize : cam.n_rows) >= 0x7FFFFFFFull)
+        return fail(RTGPU_ERR_OUT_OF_MEMORY, "the wavefront family indexes at most 2^31 - 1 pixels per launch");
     if (ctx->wf_cap_rays == 0 || (double)(ctx->wf_bytes_rays / sizeof(rt::WfRay<T>)) < WF_RAYS_PER_PIXEL * (double)pixels / 2) {
         int st = wavefront_reserve<T>(ctx, pixels, 1.0);
         if (st != RTGPU_OK) return st;
