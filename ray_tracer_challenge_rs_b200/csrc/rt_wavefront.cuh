@@ -36,8 +36,11 @@
 namespace rt {
 
 // A queued hit: the radiance ray, where it hit, and whose child it is.
+#ifndef RT_WF_RAY_ALIGN
+#define RT_WF_RAY_ALIGN 16
+#endif
 template <typename T>
-struct WfRay {
+struct alignas(RT_WF_RAY_ALIGN) WfRay {
     T ox, oy, oz, dx, dy, dz;
     T t;         // hit distance (Intersections::hit, intersections.rs:13-18)
     int pos;     // sorted position of the hit shape
@@ -49,7 +52,7 @@ struct WfRay {
 };
 
 template <typename T>
-struct alignas(32) WfNode {  // f64: 96 bytes = three 32-byte sectors exactly (104 unaligned bytes cost the combine pass 1.9x its payload in DRAM reads)
+struct alignas(32) WfNode {  // f64: 96 bytes = three 32-byte sectors exactly
     int link;         // >= 0: the parent node; < 0: a level-0 node, ~link is the output index of its pixel
     int slot_flags;   // bit 0: slot in the parent (0 reflected, 1 refracted); bit 1: Schlick blend (world.rs:59)
     T k_parent;       // scale applied to this node's colour when it is handed to the parent (world.rs:127,156)
