@@ -477,7 +477,10 @@ def run_b200(args):
 
         cscene, ccam = flat.as_c(), camera_to_c(camera)
         e2e_gpus = max(1, min(world, lib.rtgpu_device_count()))
-        opts = abi.RtgpuOpts(abi.PRECISION_F64 if args.precision == "f64" else abi.PRECISION_F32, args.max_depth, e2e_gpus, 16, family_flag)
+        # one device: the band height only sets the granularity of the two overlapped chunks; several devices: the same
+        # 4-row bands as the device-resident leg, so that no device ends up with a visibly dearer share of the rows
+        e2e_band_rows = int(os.environ.get("RTGPU_BENCH_E2E_BAND_ROWS", "16" if e2e_gpus == 1 else "4"))
+        opts = abi.RtgpuOpts(abi.PRECISION_F64 if args.precision == "f64" else abi.PRECISION_F32, args.max_depth, e2e_gpus, e2e_band_rows, family_flag)
         st = abi.RtgpuStats()
 
         def one_frame():
@@ -499,7 +502,7 @@ def run_b200(args):
         e2e = {"value": st.as_dict()["rays"] / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_frame": e2e_ms,
                "h2d_bytes_per_step": scene_bytes * e2e_gpus + 256 * e2e_gpus, "d2h_bytes_per_step": n_px * 3 * elem + 48 * e2e_gpus,
                "n_gpus": e2e_gpus,
-               "call": "rtgpu_render (scene pack + upload, kernel on N devices in 16-row bands, D2H of the full f64 Canvas into pinned host memory)",
+               "call": "rtgpu_render (scene pack + upload, kernel on N devices in %d-row bands, D2H of the full f64 Canvas into pinned host memory)" % e2e_band_rows,
                "kernel_ms_max_over_devices": st.kernel_ms, "family": last_family()}
         assert st.as_dict()["rays"] == rays, (st.as_dict(), stats)  # same kernel, same rays as the device-resident leg
         # ---- pixel identity across N (driver-readable): the N-GPU frames of both legs against a 1-GPU render ----

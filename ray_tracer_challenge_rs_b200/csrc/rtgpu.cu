@@ -1379,18 +1379,36 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
     if (st != RTGPU_OK) return st;
     CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
     if ((st = publish_status(ctx)) != RTGPU_OK) return st;
-    // compact band b (rows [b*band_rows, ...)) of this shard -> image rows of band (b*shard_count + shard_index)
-    for (uint32_t k = 0; k < n_rows; k += sel.band_rows) {
-        const uint32_t rows_here = std::min(sel.band_rows, n_rows - k);
-        const uint32_t y = selected_row(sel, k);
-        if (out_rgb)
-            CUDA_TRY(cudaMemcpyAsync((char*)out_rgb + (size_t)y * row_rgb, (char*)ctx->d_out + (size_t)k * row_rgb,
-                                     row_rgb * rows_here, cudaMemcpyDeviceToHost, ctx->stream));
-        if (out_rgb8)
-            CUDA_TRY(cudaMemcpyAsync(out_rgb8 + (size_t)y * row_rgb8, ctx->d_out8 + (size_t)k * row_rgb8, row_rgb8 * rows_here,
-                                     cudaMemcpyDeviceToHost, ctx->stream));
+    // Pageable destination: both families stage and copy the same bytes, and a pageable copy (5-10 ms for a 1080p f64
+    // frame, +-1 ms from run to run) would drown the difference between the kernels: the calibration times the kernels.
+    const bool trial_on_kernels = trial && !pinned;
+    if (trial_on_kernels) tune_end(ctx, ctx->stream, key, family);
+    // compact band q of this shard -> image band (q * shard_count + shard_index): the bands are periodic in the image,
+    // so ONE strided copy moves all complete bands (a call per band cost ~3 µs each: 34 calls per device for 4-row
+    // bands of a 1080p frame on 8 devices), and one plain copy the partial last band
+    {
+        const uint32_t full_bands = n_rows / sel.band_rows, tail_rows = n_rows % sel.band_rows;
+        const size_t first_row = (size_t)sel.shard_index * sel.band_rows, period_rows = (size_t)sel.shard_count * sel.band_rows;
+        if (out_rgb) {
+            if (full_bands)
+                CUDA_TRY(cudaMemcpy2DAsync((char*)out_rgb + first_row * row_rgb, period_rows * row_rgb, ctx->d_out, (size_t)sel.band_rows * row_rgb,
+                                           (size_t)sel.band_rows * row_rgb, full_bands, cudaMemcpyDeviceToHost, ctx->stream));
+            if (tail_rows)
+                CUDA_TRY(cudaMemcpyAsync((char*)out_rgb + (first_row + (size_t)full_bands * period_rows) * row_rgb,
+                                         (char*)ctx->d_out + (size_t)full_bands * sel.band_rows * row_rgb, (size_t)tail_rows * row_rgb, cudaMemcpyDeviceToHost,
+                                         ctx->stream));
+        }
+        if (out_rgb8) {
+            if (full_bands)
+                CUDA_TRY(cudaMemcpy2DAsync(out_rgb8 + first_row * row_rgb8, period_rows * row_rgb8, ctx->d_out8, (size_t)sel.band_rows * row_rgb8,
+                                           (size_t)sel.band_rows * row_rgb8, full_bands, cudaMemcpyDeviceToHost, ctx->stream));
+            if (tail_rows)
+                CUDA_TRY(cudaMemcpyAsync(out_rgb8 + (first_row + (size_t)full_bands * period_rows) * row_rgb8,
+                                         ctx->d_out8 + (size_t)full_bands * sel.band_rows * row_rgb8, (size_t)tail_rows * row_rgb8, cudaMemcpyDeviceToHost,
+                                         ctx->stream));
+        }
     }
-    if (trial) tune_end(ctx, ctx->stream, key, family);  // the copies belong to this path's cost
+    if (trial && !trial_on_kernels) tune_end(ctx, ctx->stream, key, family);  // pinned: the copies belong to this path's cost
     return RTGPU_OK;
 }
 
