@@ -1386,7 +1386,19 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
     // compact band q of this shard -> image band (q * shard_count + shard_index): the bands are periodic in the image,
     // so ONE strided copy moves all complete bands (a call per band cost ~3 µs each: 34 calls per device for 4-row
     // bands of a 1080p frame on 8 devices), and one plain copy the partial last band
-    {
+    static const bool per_band_copies = getenv("RTGPU_PER_BAND_COPIES") != nullptr;  // A/B switch, off by default
+    if (per_band_copies) {
+        for (uint32_t k = 0; k < n_rows; k += sel.band_rows) {
+            const uint32_t rows_here = std::min(sel.band_rows, n_rows - k);
+            const uint32_t y = selected_row(sel, k);
+            if (out_rgb)
+                CUDA_TRY(cudaMemcpyAsync((char*)out_rgb + (size_t)y * row_rgb, (char*)ctx->d_out + (size_t)k * row_rgb, row_rgb * rows_here,
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+            if (out_rgb8)
+                CUDA_TRY(cudaMemcpyAsync(out_rgb8 + (size_t)y * row_rgb8, ctx->d_out8 + (size_t)k * row_rgb8, row_rgb8 * rows_here, cudaMemcpyDeviceToHost,
+                                         ctx->stream));
+        }
+    } else {
         const uint32_t full_bands = n_rows / sel.band_rows, tail_rows = n_rows % sel.band_rows;
         const size_t first_row = (size_t)sel.shard_index * sel.band_rows, period_rows = (size_t)sel.shard_count * sel.band_rows;
         if (out_rgb) {
@@ -1767,10 +1779,13 @@ int rtgpu_render(const rtgpu_scene* scene, const rtgpu_camera* camera, const rtg
         int status = RTGPU_OK;
         std::string error;
         rtgpu_stats stats{};
+        double t_start = 0, t_enqueued = 0, t_done = 0;  // ms since the call began (RTGPU_TRACE=1 prints them)
     };
+    static const bool trace = getenv("RTGPU_TRACE") != nullptr;
     std::vector<DeviceJob> jobs(n_gpus);
     auto work = [&](int g) {
         DeviceJob& job = jobs[g];
+        job.t_start = wall_ms() - t0;
         rtgpu_rows rows;
         rows.band_rows = n_gpus == 1 ? 0u : band_rows;
         rows.shard_index = (uint32_t)g;
@@ -1782,11 +1797,20 @@ int rtgpu_render(const rtgpu_scene* scene, const rtgpu_camera* camera, const rtg
             if (rc == RTGPU_OK) cache[g]->uploaded_input_hash = input_hash;
         }
         if (rc == RTGPU_OK) rc = enqueue_host_render(cache[g], camera, opts, &rows, out_rgb, out_rgb8);
+        job.t_enqueued = wall_ms() - t0;
         if (rc == RTGPU_OK) rc = finish_host_render(cache[g], camera, opts, &rows, out_rgb, out_rgb8, stats ? &job.stats : nullptr);
+        job.t_done = wall_ms() - t0;
         job.status = rc;
         if (rc != RTGPU_OK) job.error = g_last_error;
     };
+    const double t_dispatch = wall_ms() - t0;
     worker_pool().run(n_gpus, work);
+    if (trace) {
+        fprintf(stderr, "[rtgpu] one-shot: dispatch at %.3f ms, joined at %.3f ms\n", t_dispatch, wall_ms() - t0);
+        for (int g = 0; g < n_gpus; ++g)
+            fprintf(stderr, "[rtgpu]   device %d: start %.3f enqueued %.3f done %.3f kernels %.3f ms\n", g, jobs[g].t_start, jobs[g].t_enqueued, jobs[g].t_done,
+                    jobs[g].stats.kernel_ms);
+    }
     for (int g = 0; g < n_gpus; ++g) {
         if (jobs[g].status != RTGPU_OK) {
             g_last_error = jobs[g].error;
