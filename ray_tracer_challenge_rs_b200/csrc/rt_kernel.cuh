@@ -53,6 +53,9 @@ namespace rt {
 #ifndef RT_CULL
 #define RT_CULL 1  // bounding-sphere pre-test in the intersection loop (exact results either way)
 #endif
+#ifndef RT_CULL_F32
+#define RT_CULL_F32 1  // f64 kernels: the pre-test runs in single precision with proven margins (trace_unified); exact results either way
+#endif
 
 #ifndef RT_STRICT_SIGNED_ZERO
 // 1: keep the reference's `0.0 + ...` fold seeds and `+ m[r][3] * w` terms of Matrix*Point/Vector
@@ -238,6 +241,7 @@ struct SceneView {
     RT_DEV const int* pattern_meta(uint32_t p) const { return I() + L.pat_meta_off + p * PAT_INTS; }
     RT_DEV const T* light(uint32_t l) const { return R() + L.light_off + (size_t)l * LIGHT_REALS; }
     RT_DEV const T* cull(uint32_t pos) const { return R() + L.cull_off + (size_t)pos * CULL_REALS; }
+    RT_DEV const float4* cull32(uint32_t pos) const { return reinterpret_cast<const float4*>(I() + L.cull32_off) + pos; }
     RT_DEV T cull_shrink() const { return sizeof(T) == 8 ? (T)L.cull_shrink64 : (T)L.cull_shrink32; }
 };
 
@@ -903,6 +907,44 @@ struct CullCursor<T, false> {  // tables in global memory
     RT_DEV void load(T& x, T& y, T& z, T& w) const { load_cull(at, x, y, z, w); }
 };
 
+// The same cursor over the single-precision cull records (16 bytes each, int blob).
+template <bool SMEM>
+struct Cull32Cursor;
+template <>
+struct Cull32Cursor<true> {
+    uint32_t at, end;
+    template <typename SV>
+    RT_DEV Cull32Cursor(const SV& sv, uint32_t first, uint32_t n) {
+        at = (uint32_t)__cvta_generic_to_shared(sv.cull32(first));
+        end = at + n * 16u;
+        asm volatile("" : "+r"(end));
+    }
+    RT_DEV bool done() const { return at == end; }
+    RT_DEV void next() { at += 16u; }
+    RT_DEV void finish() { at = end - 16u; }
+    RT_DEV uint32_t position(uint32_t n) const { return n - (end - at) / 16u; }
+    RT_DEV void load(float& x, float& y, float& z, float& w) const {
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(at));
+    }
+};
+template <>
+struct Cull32Cursor<false> {
+    const float4 *at, *end;
+    template <typename SV>
+    RT_DEV Cull32Cursor(const SV& sv, uint32_t first, uint32_t n) {
+        at = sv.cull32(first);
+        end = at + n;
+    }
+    RT_DEV bool done() const { return at == end; }
+    RT_DEV void next() { ++at; }
+    RT_DEV void finish() { at = end - 1; }
+    RT_DEV uint32_t position(uint32_t n) const { return n - (uint32_t)(end - at); }
+    RT_DEV void load(float& x, float& y, float& z, float& w) const {
+        const float4 a = *at;
+        x = a.x; y = a.y; z = a.z; w = a.w;
+    }
+};
+
 // World::collect_intersections (world.rs:25-35) over the uniform list.  One loop with a warp-uniform switch on
 // the shape type: the pre-test, the object-space transform and the query bookkeeping exist ONCE in the instruction
 // stream instead of once per shape type.  The kernels are bound by instruction supply (GPC instruction cache
@@ -983,6 +1025,59 @@ RT_DEV void trace_unified(const SceneView<T, SMEM>& sv, const Ray<T>& ray, Trace
     // evaluated without short-circuits (one data-dependent branch instead of two), and a shadow query that has found
     // its blocker leaves by moving the cursor to the last record instead of a `break` (no per-iteration
     // BSSY / BSYNC pair around the body).
+#if RT_CULL_F32
+    if constexpr (sizeof(T) == 8) {
+        // The f64 kernels run the pre-test in SINGLE precision: its ~15 arithmetic instructions per shape were more than
+        // half of all FP64-pipe work of a frame (half rate, 8.4-cycle dependent latency), and a pre-test only has to be
+        // safe, not exact.  Safe means: it culls only when, in real arithmetic, the ray's line misses the record's sphere
+        // or the sphere lies wholly behind the origin.  With u = 2^-24, M = max(|origin|_inf, |any centre|_inf):
+        //   * rounding origin and centre to f32 and subtracting moves oc by at most eps = 4uM per component
+        //     (eta = sqrt(3) eps in length); rounding the direction tilts the line by <= 2u, i.e. moves it by <= 2u|oc| at
+        //     the centre.  So the true distance line-centre is >= the f32-input one - m, m = eta + 2u|oc|;
+        //   * (r + m)^2 <= r^2 (1 + 2^-10) + 1025 m^2 and 1025 m^2 <= 2050 eta^2 + 8200 u^2 |oc|^2 <= 2^-30.4 M^2
+        //     (|oc|^2 <= 12 M^2): the packer pads r^2 by 2^-9, the loop adds E = 2^-29 M^2;
+        //   * evaluating c2 dd - bq^2 in f32 (fma dots) is off by < 16u c2 dd: the factor 1 - 2^-18 = 1 - 64u on c2
+        //     pays for it, including the roundings of the comparison itself;
+        //   * "behind": once the origin is outside by these margins (c2 - r^2 >= E/2), a centre whose f32 bq is negative
+        //     but whose true bq is not has bq^2 <= (eta + 5u|oc|)^2 dd < E dd / 2 <= dd (c2 - r^2): no real intersection.
+        // NaN, infinities and directions whose dd leaves [1e-30, 1e30] make every comparison false or E infinite: no
+        // culling.  The exact tests that follow are the f64 ones, so the frame is the same bits with or without this.
+        // (Tried: two shapes per iteration with the packed FFMA2 / FADD2 / FMUL2 of sm_100a — 15.5 instead of 24
+        // instructions per culled shape, level 0 of the cover frame 7 % faster, but at depth some lane survives in nearly
+        // every pair and the two-way rare path costs what the pre-test saves: profiles/r2_notes.md.)
+        Cull32Cursor<SMEM> cur(sv, 0u, n);
+        float ox = (float)ray.o.x, oy = (float)ray.o.y, oz = (float)ray.o.z;
+        float dx = (float)ray.d.x, dy = (float)ray.d.y, dz = (float)ray.d.z;
+        // opaque: otherwise ptxas re-converts the six doubles in every iteration (F2F on the FP64 pipe) to save registers
+        keep_in_register(ox); keep_in_register(oy); keep_in_register(oz);
+        keep_in_register(dx); keep_in_register(dy); keep_in_register(dz);
+        float dd = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        const float m = fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fmaxf(fabsf(oz), sv.L.cull_coord_max));
+        float pad = (m * m) * 0x1p-29f;
+        if (!(dd > 1.0e-30f && dd < 1.0e30f) || !(m < 1.0e18f)) pad = __int_as_float(0x7f800000);
+        float behind_below = acc.mode == MODE_CONTAINER ? -__int_as_float(0x7f800000) : 0.0f;
+        float shrink = 1.0f - 0x1p-18f;
+        keep_in_register(behind_below);
+        keep_in_register(pad);
+        keep_in_register(dd);
+        keep_in_register(shrink);
+        for (; !cur.done(); cur.next()) {
+            float cx, cy, cz, r2;
+            cur.load(cx, cy, cz, r2);
+            const float ocx = cx - ox, ocy = cy - oy, ocz = cz - oz;
+            const float bq = fmaf(ocz, dz, fmaf(ocy, dy, ocx * dx));
+            const float c2 = fmaf(ocz, ocz, fmaf(ocy, ocy, ocx * ocx));
+            const float ex = fmaf(c2, shrink, -(r2 + pad));
+            const bool outside = ex > 0.0f, behind = bq < behind_below, misses = ex * dd > bq * bq;
+            if (outside & (behind | misses)) continue;
+            uint32_t pos = cur.position(n);
+            asm volatile("" : "+r"(pos));
+            exact_test<T, FULL>(sv, pos, ray, acc);
+            if (SHADOW_EXIT && acc.mode == MODE_SHADOW && acc.best_pos >= 0) cur.finish();
+        }
+        return;
+    }
+#endif
     CullCursor<T, SMEM> cur(sv, 0u, n);
     // "the centre is behind the origin" only culls when negative distances are of no interest (everything but the
     // container walk): comparing against -max instead of 0 switches it off without a mode test in the loop

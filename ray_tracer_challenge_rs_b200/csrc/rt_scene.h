@@ -96,6 +96,8 @@ struct SceneLayout {
     uint32_t mat_meta_off, pat_meta_off, bvh_meta_off;  // offsets into the int blob, in int32
     uint32_t bvh32_off;                             // single-precision BVH nodes (BVH32_WORDS each), int blob, multiple of 4
     float bvh_coord_max;                            // largest |coordinate| of any BVH box (sizes the origin margin of box_hit32)
+    uint32_t cull32_off;                            // single-precision cull records (4 words each: centre, padded radius^2), int blob, multiple of 4
+    float cull_coord_max;                           // largest |coordinate| of any finite cull-sphere centre, rounded up
     uint32_t n_bvh_nodes;                           // > 0: the bounded shapes are reached through a BVH
     int32_t bvh_root;                               // root reference (>= 0 node, < 0 single leaf)
     uint32_t n_reals, n_ints;                       // blob sizes

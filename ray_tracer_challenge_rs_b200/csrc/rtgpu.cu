@@ -367,7 +367,8 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     lay.pat_meta_off = lay.mat_meta_off + M * rt::MAT_INTS;
     lay.bvh_meta_off = (lay.pat_meta_off + Q * rt::PAT_INTS + 1u) & ~1u;
     lay.bvh32_off = (lay.bvh_meta_off + lay.n_bvh_nodes * rt::BVH_INTS + 3u) & ~3u;
-    lay.n_ints = lay.bvh32_off + lay.n_bvh_nodes * rt::BVH32_WORDS;
+    lay.cull32_off = (lay.bvh32_off + lay.n_bvh_nodes * rt::BVH32_WORDS + 3u) & ~3u;
+    lay.n_ints = lay.cull32_off + S * 4u;
     lay.n_ints = (lay.n_ints + 3u) & ~3u;
     if ((uint64_t)S * rt::SHAPE_REALS + (uint64_t)n_tri * rt::TRI_REALS + (uint64_t)S * rt::CULL_REALS + (uint64_t)lay.n_bvh_nodes * rt::BVH_REALS > 0xF0000000ull)
         return fail(RTGPU_ERR_UNSUPPORTED, "scene too large for 32-bit blob offsets (%u shapes)", S);
@@ -398,6 +399,25 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
         m[3] = (int)cls;
         m[4] = -1;
         bounding_sphere(s, i, R + lay.cull_off + (size_t)pos * rt::CULL_REALS);
+        {
+            // single-precision copy for the f64 kernels' pre-test (rt_kernel.cuh trace_unified): {cx, cy, cz, r2}, centre
+            // rounded to nearest (the kernel's margin covers that), radius^2 padded by 2^-9 and rounded up; an infinite
+            // or unrepresentable record stays "never culled"
+            const double* c64 = R + lay.cull_off + (size_t)pos * rt::CULL_REALS;
+            float c32[4];
+            for (int k = 0; k < 3; ++k) c32[k] = (float)c64[k];
+            const double padded = c64[3] * (1.0 + 0x1p-9);
+            float r2 = (float)padded;
+            if ((double)r2 < padded) r2 = std::nextafterf(r2, std::numeric_limits<float>::infinity());
+            c32[3] = r2;
+            if (std::isfinite(c64[3]))
+                for (int k = 0; k < 3; ++k) {
+                    const float a = std::nextafterf(std::fabs(c32[k]), std::numeric_limits<float>::infinity());
+                    if (!std::isfinite(a)) lay.cull_coord_max = std::numeric_limits<float>::infinity();  // the kernel then never culls
+                    else if (a > lay.cull_coord_max) lay.cull_coord_max = a;
+                }
+            memcpy(I + lay.cull32_off + (size_t)pos * 4, c32, sizeof(c32));
+        }
         if (s->shape_type[i] == RTGPU_TRIANGLE) {
             const size_t t = (size_t)s->shape_triangle[i] * 3;
             m[4] = (int)tri_slot;
@@ -919,12 +939,52 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
     CUDA_TRY(cudaMemsetAsync(ctx->d_wf_priv, 0, rt::NUM_COUNTERS * sizeof(unsigned long long), stream));
     (void)d_counters;
     rt::WfNode<T>* nodes = reinterpret_cast<rt::WfNode<T>*>(ctx->d_wf_nodes);
+    const char* sort_env = getenv("RTGPU_SORT_EXPERIMENT");
+    const bool sort_experiment = sort_env != nullptr;
+    const int sort_key = sort_env ? atoi(sort_env) : 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (sort_experiment) {
+        CUDA_TRY(cudaEventCreate(&ev0));
+        CUDA_TRY(cudaEventCreate(&ev1));
+    }
     for (int level = 0; level < levels; ++level) {
         const rt::WfRay<T>* in = reinterpret_cast<const rt::WfRay<T>*>(ctx->d_wf_rays[level & 1]);
         rt::WfRay<T>* out = reinterpret_cast<rt::WfRay<T>*>(ctx->d_wf_rays[(level + 1) & 1]);
+        if (sort_experiment) CUDA_TRY(cudaEventRecord(ev0, stream));
         level_kernel<<<grid, RT_WF_THREADS, smem, stream>>>(d_reals, ctx->d_ints, lay, cam, level, in, out, (unsigned)ctx->wf_cap_rays, nodes,
                                                             (unsigned)ctx->wf_cap_nodes, ctx->d_wf_counts, d_out, d_out8, ctx->d_wf_priv);
         CUDA_TRY(cudaGetLastError());
+        if (sort_experiment) {
+            // EXPERIMENT (RTGPU_SORT_EXPERIMENT=key): time the level, then reorder the next level's queue on the host.
+            // Queue entries carry their parent link, so any order renders the same frame; this measures what a
+            // device-side binning of the queue would be worth before anyone builds it.
+            CUDA_TRY(cudaEventRecord(ev1, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, ev0, ev1));
+            rt::WfCounts h;
+            CUDA_TRY(cudaMemcpy(&h, ctx->d_wf_counts, sizeof(h), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[rtgpu] sort experiment (key %d): level %d took %.4f ms; next queue %u + %u\n", sort_key, level, ms, h.n_rays[level + 1], h.n_back[level + 1]);
+            auto reorder = [&](rt::WfRay<T>* d_first, unsigned count) -> int {
+                if (count < 2 || sort_key == 0) return RTGPU_OK;
+                std::vector<rt::WfRay<T>> q(count);
+                CUDA_TRY(cudaMemcpy(q.data(), d_first, (size_t)count * sizeof(rt::WfRay<T>), cudaMemcpyDeviceToHost));
+                auto oct = [](const rt::WfRay<T>& r) { return (r.dx < 0 ? 1 : 0) | (r.dy < 0 ? 2 : 0) | (r.dz < 0 ? 4 : 0); };
+                std::stable_sort(q.begin(), q.end(), [&](const rt::WfRay<T>& a, const rt::WfRay<T>& b) {
+                    if (sort_key == 1) return a.pos < b.pos;                                            // hit shape
+                    if (sort_key == 2) return a.pos != b.pos ? a.pos < b.pos : a.slot < b.slot;         // hit shape, then reflect / refract
+                    if (sort_key == 3) return a.slot < b.slot;                                          // reflect / refract only
+                    return a.pos != b.pos ? a.pos < b.pos : (a.slot != b.slot ? a.slot < b.slot : oct(a) < oct(b));  // + direction octant
+                });
+                CUDA_TRY(cudaMemcpy(d_first, q.data(), (size_t)count * sizeof(rt::WfRay<T>), cudaMemcpyHostToDevice));
+                return RTGPU_OK;
+            };
+            if (level + 1 < levels && !h.overflow) {
+                int st = reorder(out, h.n_rays[level + 1]);
+                if (st == RTGPU_OK) st = reorder(out + ctx->wf_cap_rays - h.n_back[level + 1], h.n_back[level + 1]);
+                if (st != RTGPU_OK) return st;
+            }
+        }
         if (debug_sync) {
             const double t0 = wall_ms();
             CUDA_TRY(cudaStreamSynchronize(stream));
@@ -933,6 +993,10 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
             fprintf(stderr, "[rtgpu] wavefront level %d done (+%.2f ms wait): next queue %u front + %u back, %u nodes, overflow %u\n", level,
                     wall_ms() - t0, h.n_rays[level + 1], h.n_back[level + 1], h.n_nodes, h.overflow);
         }
+    }
+    if (sort_experiment) {
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
     }
     for (int level = levels - 1; level >= 0; --level)
         rt::wf_combine_kernel<T><<<ctx->sm_count * 4, 256, 0, stream>>>(nodes, ctx->d_wf_counts, level, (unsigned)ctx->wf_cap_nodes, d_out, d_out8);
