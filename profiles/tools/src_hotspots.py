@@ -106,6 +106,21 @@ def main():
     print("opcode classes (share of warp instructions | of stall samples):")
     for c, v in sorted(per_class.items(), key=lambda kv: -kv[1][0]):
         print(f"  {c:16s} {v[0] / tot_i * 100:6.2f}%  {v[1] / max(tot_s, 1) * 100:6.2f}%")
+    per_op = collections.Counter()
+    for k in range(n):
+        op = ncu[k][0]
+        op = op.split()[0] if not op.startswith("@") else op.split()[1]
+        per_op[op.split(".")[0]] += ncu[k][1]
+    print("opcodes by executed warp instructions:", ", ".join(f"{o} {c / tot_i * 100:.1f}%" for o, c in per_op.most_common(28)))
+    only = os.environ.get("HOT_CLASS")  # e.g. HOT_CLASS=integer/move: the source lines where that class executes most
+    if only:
+        cls_line = collections.Counter()
+        for k in range(n):
+            if classify(ncu[k][0]) == only:
+                cls_line[sass[k][2]] += ncu[k][1]
+        print(f"class {only} by source line (share of ALL warp instructions):")
+        for key, c in cls_line.most_common(top):
+            print(f"  {key[0]}:{key[1]:<5d} {c / tot_i * 100:6.2f}%")
     print("by source line (warp instrs | stall samples | threads per instr | #SASS):")
     for key, v in sorted(per_line.items(), key=lambda kv: -kv[1][2])[:top]:
         print(f"  {key[0]}:{key[1]:<5d} {v[0] / tot_i * 100:6.2f}%  {v[2] / max(tot_s, 1) * 100:6.2f}%  {v[1] / max(v[0], 1):5.1f}  ({v[3]})")

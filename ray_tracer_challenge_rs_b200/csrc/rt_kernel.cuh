@@ -974,9 +974,11 @@ RT_DEV void exact_test(const SceneView<T, SMEM>& sv, uint32_t pos, const Ray<T>&
     case 0: k = local_intersect<T, 0>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
     case 1: k = local_intersect<T, 1>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
     case 2: k = local_intersect<T, 2>(local, g, meta.z, nullptr, t0, t1, t2, t3); break;
-    case 3: if (FULL) k = local_intersect<T, 3>(local, g, meta.z, nullptr, t0, t1, t2, t3); else t0 = t1 = t2 = t3 = T(0); break;
-    case 4: if (FULL) k = local_intersect<T, 4>(local, g, meta.z, nullptr, t0, t1, t2, t3); else t0 = t1 = t2 = t3 = T(0); break;
-    default: if (FULL) k = local_intersect<T, 5>(local, g, meta.z, sv.triangle(pos), t0, t1, t2, t3); else t0 = t1 = t2 = t3 = T(0); break;
+    // !FULL kernels are only launched for scenes without cylinders, cones and triangles: nothing to consume.  (Giving the
+    // distances dummy zeros instead put two register-pair clears into every iteration of the caller's shape loop.)
+    case 3: if (FULL) k = local_intersect<T, 3>(local, g, meta.z, nullptr, t0, t1, t2, t3); else return; break;
+    case 4: if (FULL) k = local_intersect<T, 4>(local, g, meta.z, nullptr, t0, t1, t2, t3); else return; break;
+    default: if (FULL) k = local_intersect<T, 5>(local, g, meta.z, sv.triangle(pos), t0, t1, t2, t3); else return; break;
     }
     consume<T, 4>(acc, k, t0, t1, t2, t3, (int)pos, meta);
 }

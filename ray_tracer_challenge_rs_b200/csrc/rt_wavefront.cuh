@@ -171,7 +171,14 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
     // behind the staged tables: the warps' scratch for the pair-list trace (if compiled in), then WF_PARK_REALS columns
     // of per-thread node state
     PairScratch<T>* const ws = reinterpret_cast<PairScratch<T>*>(sv.scratch()) + (threadIdx.x >> 5);
-    T* const park = reinterpret_cast<T*>(sv.scratch() + ((RT_WF_PAIRS && !BVH) ? (RT_WF_THREADS / 32) * sizeof(PairScratch<T>) : 0)) + threadIdx.x;
+    // The thread's column base as an opaque 32-bit offset into the dynamic shared window: ptxas otherwise rebuilds the
+    // address from the layout constants at every use (38 sites, 3.4 % of the level-0 instructions), and an opaque POINTER
+    // would turn the accesses into generic loads.
+    extern __shared__ __align__(16) unsigned char rt_scene_smem[];
+    uint32_t park_at = (uint32_t)(sv.scratch() - rt_scene_smem) + (uint32_t)((RT_WF_PAIRS && !BVH) ? (RT_WF_THREADS / 32) * sizeof(PairScratch<T>) : 0) +
+                       threadIdx.x * (uint32_t)sizeof(T);
+    asm volatile("" : "+r"(park_at));
+    T* const park = reinterpret_cast<T*>(rt_scene_smem + park_at);
     if (RT_WF_PAIRS && !BVH) {
         ws->owner[lane] = 0u;
         __syncwarp();
