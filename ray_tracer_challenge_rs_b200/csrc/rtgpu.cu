@@ -60,6 +60,7 @@ struct PackedScene {
     rt::SceneLayout layout;
     bool has_cyl_cone_tri = false;
     bool has_secondary = false;  // some material is reflective or transparent: rays beyond primary + shadow exist
+    uint32_t secondary_shapes = 0;  // shapes whose material is reflective or transparent
     uint64_t fingerprint = 0;    // of the packed blobs (sampled for large scenes): the tuner's notion of "same scene"
 };
 
@@ -343,6 +344,10 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     for (uint32_t m = 0; m < M; ++m) {
         const double* prm = s->mat_params + (size_t)m * RTGPU_MAT_PARAM_COUNT;
         if (prm[4] > 0.0 || prm[5] > 0.0) out->has_secondary = true;  // reflective, transparency (world.rs:121, 137)
+    }
+    for (uint32_t i = 0; i < S; ++i) {
+        const double* prm = s->mat_params + (size_t)s->shape_material[i] * RTGPU_MAT_PARAM_COUNT;
+        if (prm[4] > 0.0 || prm[5] > 0.0) out->secondary_shapes++;
     }
     const uint32_t n_nodes = (uint32_t)bvh.nodes.size();
     lay.n_bvh_nodes = use_bvh ? std::max(n_nodes, 1u) : 0u;  // a single bounded shape still gets one (half-empty) node
@@ -644,6 +649,9 @@ struct rtgpu_context {
     void* d_wf_nodes = nullptr;
     rt::WfCounts* d_wf_counts = nullptr;
     unsigned long long* d_wf_priv = nullptr;  // the frame's own work counters, committed to the caller's once it is complete
+    unsigned long long* d_wf_keys = nullptr;  // binned queues (rt_wavefront.cuh wf_bin_kernel): (bin, rank) per queue entry ...
+    unsigned* d_wf_perm = nullptr;            // ... and the permutation the next level consumes its queue through
+    size_t wf_bin_entries = 0;                // entries both arrays hold
     size_t wf_cap_rays = 0, wf_cap_nodes = 0;  // in elements
     size_t wf_bytes_rays = 0, wf_bytes_nodes = 0;
     bool wf_used = false;  // the last launch took the wavefront path (overflow must be checked after it)
@@ -653,6 +661,7 @@ struct rtgpu_context {
     cudaEvent_t ev_chunk = nullptr, ev_copied = nullptr;
     // kernel-family tuner (FAMILY_AUTO): per (scene, frame shape, path) the best time of each family
     bool has_secondary = false;
+    uint32_t secondary_shapes = 0;
     uint64_t scene_fingerprint = 0;
     struct TuneEntry {
         uint64_t key = 0;
@@ -857,6 +866,12 @@ void tune_end(rtgpu_context* ctx, cudaStream_t stream, uint64_t key, int family)
 // once (the buffers are kept).  Small on purpose: the first frame of a process pays for allocating and first touching
 // them (3 + 5 per pixel = 1.7 GB at 1080p cost a cold call ~1 s and its first frame 15 ms instead of 2).
 constexpr double WF_RAYS_PER_PIXEL = 1.0, WF_NODES_PER_PIXEL = 2.0;
+// Binned queues pay where the deeper launches are large and bound by divergence over a longer shape list: at least half
+// of the shapes reflective or transparent (cover 18 of 19: -4.4 %; reflect_refract 7 of 13: -2.5 %; table 6 of 18: +-0;
+// cylinders 3 of 11: +5 %), at least 8 shapes (scenes of 3-6 shapes: +6..8 % when forced on) and 2^18 pixels per launch
+// (smaller launches are bound by launch latency); everything else stays in arrival order.  profiles/r2_notes.md.
+constexpr uint64_t WF_BIN_MIN_PIXELS = 1u << 18;
+constexpr uint32_t WF_BIN_MIN_SHAPES = 8;
 
 template <typename T>
 int wavefront_reserve(rtgpu_context* ctx, uint64_t pixels, double growth) {
@@ -939,52 +954,32 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
     CUDA_TRY(cudaMemsetAsync(ctx->d_wf_priv, 0, rt::NUM_COUNTERS * sizeof(unsigned long long), stream));
     (void)d_counters;
     rt::WfNode<T>* nodes = reinterpret_cast<rt::WfNode<T>*>(ctx->d_wf_nodes);
-    const char* sort_env = getenv("RTGPU_SORT_EXPERIMENT");
-    const bool sort_experiment = sort_env != nullptr;
-    const int sort_key = sort_env ? atoi(sort_env) : 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    if (sort_experiment) {
-        CUDA_TRY(cudaEventCreate(&ev0));
-        CUDA_TRY(cudaEventCreate(&ev1));
+    // Binned queues for scenes whose whole shape list fits the bins (rt_wavefront.cuh RT_WF_BINS); small launches are
+    // bound by launch latency, not by divergence, and skip the extra kernel per level.  RTGPU_WF_BINS=0 / 1 forces it.
+    bool binned = !BVH && lay.type_begin[rt::NUM_SHAPE_TYPES] <= RT_WF_BINS / 2 && lay.type_begin[rt::NUM_SHAPE_TYPES] >= WF_BIN_MIN_SHAPES && pixels >= WF_BIN_MIN_PIXELS &&
+                  2u * ctx->secondary_shapes >= lay.n_shapes;
+    if (const char* e = getenv("RTGPU_WF_BINS"); e && *e) binned = !BVH && e[0] == '1';
+    if (binned && ctx->wf_bin_entries < ctx->wf_cap_rays) {
+        if (ctx->d_wf_keys) cudaFree(ctx->d_wf_keys);
+        if (ctx->d_wf_perm) cudaFree(ctx->d_wf_perm);
+        ctx->d_wf_keys = nullptr;
+        ctx->d_wf_perm = nullptr;
+        ctx->wf_bin_entries = 0;
+        const size_t entries = ctx->wf_bytes_rays / sizeof(rt::WfRay<float>);  // enough for either precision
+        CUDA_TRY(cudaMalloc(&ctx->d_wf_keys, entries * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMalloc(&ctx->d_wf_perm, entries * sizeof(unsigned)));
+        ctx->wf_bin_entries = entries;
     }
     for (int level = 0; level < levels; ++level) {
         const rt::WfRay<T>* in = reinterpret_cast<const rt::WfRay<T>*>(ctx->d_wf_rays[level & 1]);
         rt::WfRay<T>* out = reinterpret_cast<rt::WfRay<T>*>(ctx->d_wf_rays[(level + 1) & 1]);
-        if (sort_experiment) CUDA_TRY(cudaEventRecord(ev0, stream));
         level_kernel<<<grid, RT_WF_THREADS, smem, stream>>>(d_reals, ctx->d_ints, lay, cam, level, in, out, (unsigned)ctx->wf_cap_rays, nodes,
-                                                            (unsigned)ctx->wf_cap_nodes, ctx->d_wf_counts, d_out, d_out8, ctx->d_wf_priv);
+                                                            (unsigned)ctx->wf_cap_nodes, ctx->d_wf_counts, d_out, d_out8, ctx->d_wf_priv,
+                                                            (binned && level > 0) ? ctx->d_wf_perm : nullptr,
+                                                            (binned && level + 1 < levels) ? ctx->d_wf_keys : nullptr);
         CUDA_TRY(cudaGetLastError());
-        if (sort_experiment) {
-            // EXPERIMENT (RTGPU_SORT_EXPERIMENT=key): time the level, then reorder the next level's queue on the host.
-            // Queue entries carry their parent link, so any order renders the same frame; this measures what a
-            // device-side binning of the queue would be worth before anyone builds it.
-            CUDA_TRY(cudaEventRecord(ev1, stream));
-            CUDA_TRY(cudaStreamSynchronize(stream));
-            float ms = 0.f;
-            CUDA_TRY(cudaEventElapsedTime(&ms, ev0, ev1));
-            rt::WfCounts h;
-            CUDA_TRY(cudaMemcpy(&h, ctx->d_wf_counts, sizeof(h), cudaMemcpyDeviceToHost));
-            fprintf(stderr, "[rtgpu] sort experiment (key %d): level %d took %.4f ms; next queue %u + %u\n", sort_key, level, ms, h.n_rays[level + 1], h.n_back[level + 1]);
-            auto reorder = [&](rt::WfRay<T>* d_first, unsigned count) -> int {
-                if (count < 2 || sort_key == 0) return RTGPU_OK;
-                std::vector<rt::WfRay<T>> q(count);
-                CUDA_TRY(cudaMemcpy(q.data(), d_first, (size_t)count * sizeof(rt::WfRay<T>), cudaMemcpyDeviceToHost));
-                auto oct = [](const rt::WfRay<T>& r) { return (r.dx < 0 ? 1 : 0) | (r.dy < 0 ? 2 : 0) | (r.dz < 0 ? 4 : 0); };
-                std::stable_sort(q.begin(), q.end(), [&](const rt::WfRay<T>& a, const rt::WfRay<T>& b) {
-                    if (sort_key == 1) return a.pos < b.pos;                                            // hit shape
-                    if (sort_key == 2) return a.pos != b.pos ? a.pos < b.pos : a.slot < b.slot;         // hit shape, then reflect / refract
-                    if (sort_key == 3) return a.slot < b.slot;                                          // reflect / refract only
-                    return a.pos != b.pos ? a.pos < b.pos : (a.slot != b.slot ? a.slot < b.slot : oct(a) < oct(b));  // + direction octant
-                });
-                CUDA_TRY(cudaMemcpy(d_first, q.data(), (size_t)count * sizeof(rt::WfRay<T>), cudaMemcpyHostToDevice));
-                return RTGPU_OK;
-            };
-            if (level + 1 < levels && !h.overflow) {
-                int st = reorder(out, h.n_rays[level + 1]);
-                if (st == RTGPU_OK) st = reorder(out + ctx->wf_cap_rays - h.n_back[level + 1], h.n_back[level + 1]);
-                if (st != RTGPU_OK) return st;
-            }
-        }
+        if (binned && level + 1 < levels)
+            rt::wf_bin_kernel<<<ctx->sm_count * 4, 256, 0, stream>>>(ctx->d_wf_counts, level + 1, (unsigned)ctx->wf_cap_rays, ctx->d_wf_keys, ctx->d_wf_perm);
         if (debug_sync) {
             const double t0 = wall_ms();
             CUDA_TRY(cudaStreamSynchronize(stream));
@@ -993,10 +988,6 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
             fprintf(stderr, "[rtgpu] wavefront level %d done (+%.2f ms wait): next queue %u front + %u back, %u nodes, overflow %u\n", level,
                     wall_ms() - t0, h.n_rays[level + 1], h.n_back[level + 1], h.n_nodes, h.overflow);
         }
-    }
-    if (sort_experiment) {
-        cudaEventDestroy(ev0);
-        cudaEventDestroy(ev1);
     }
     for (int level = levels - 1; level >= 0; --level)
         rt::wf_combine_kernel<T><<<ctx->sm_count * 4, 256, 0, stream>>>(nodes, ctx->d_wf_counts, level, (unsigned)ctx->wf_cap_nodes, d_out, d_out8);
@@ -1180,6 +1171,7 @@ int upload_scene(rtgpu_context* ctx, const PackedScene& packed) {
     ctx->layout = lay;
     ctx->has_cyl_cone_tri = packed.has_cyl_cone_tri;
     ctx->has_secondary = packed.has_secondary;
+    ctx->secondary_shapes = packed.secondary_shapes;
     ctx->scene_fingerprint = packed.fingerprint;
     // repeated frames of similar scenes reuse the allocations (cudaFree / cudaMalloc synchronise the device)
     const size_t need_reals = std::max<size_t>(16, (size_t)lay.n_reals * sizeof(double));
@@ -1244,6 +1236,8 @@ void context_release(rtgpu_context* ctx) {
     if (ctx->d_wf_nodes) cudaFree(ctx->d_wf_nodes);
     if (ctx->d_wf_counts) cudaFree(ctx->d_wf_counts);
     if (ctx->d_wf_priv) cudaFree(ctx->d_wf_priv);
+    if (ctx->d_wf_keys) cudaFree(ctx->d_wf_keys);
+    if (ctx->d_wf_perm) cudaFree(ctx->d_wf_perm);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_chunk) cudaEventDestroy(ctx->ev_chunk);

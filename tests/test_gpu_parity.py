@@ -563,3 +563,31 @@ def test_wavefront_chunked_host_render_overflows_and_recovers(monkeypatch):
     assert np.array_equal(a.view(np.uint64), pin.array.view(np.uint64)) and np.array_equal(a8, pin8.array)
     pin.close()
     pin8.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene,width,height", [("cover", 640, 360), ("reflect_refract", 333, 201), ("refraction", 200, 150), ("cylinders", 320, 200),
+                                                ("metal", 97, 61)])
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_binned_queues_render_the_same_bits(monkeypatch, scene, width, height, precision):
+    """rt_wavefront.cuh wf_bin_kernel: consuming a level's queue grouped by (hit shape, reflected / refracted) changes
+    which entries share a warp, never a bit of the frame or a counter; forced on (RTGPU_WF_BINS=1) for frames and scenes
+    the default gate would leave in arrival order, and together with the overflow -> enlarge -> render-again path."""
+    flat, camera = load_scene_fixture(scene)
+    cam = camera.resized(width, height)
+    bits = np.uint64 if precision == "f64" else np.uint32
+    monkeypatch.setenv("RTGPU_WF_BINS", "0")
+    with Renderer(flat) as r:
+        want, want8, wstats = r.render(cam, family="wavefront", precision=precision)
+    monkeypatch.setenv("RTGPU_WF_BINS", "1")
+    with Renderer(flat) as r:
+        got, got8, stats = r.render(cam, family="wavefront", precision=precision)
+        again, again8, _ = r.render(cam, family="wavefront", precision=precision)
+    assert np.array_equal(got.view(bits), want.view(bits)) and np.array_equal(got8, want8)
+    assert np.array_equal(again.view(bits), want.view(bits)) and np.array_equal(again8, want8)
+    assert {k: stats[k] for k in COUNTERS} == {k: wstats[k] for k in COUNTERS}
+    monkeypatch.setenv("RTGPU_WF_INITIAL_SCALE", "0.02")  # queues far too small at first: binned frames overflow, grow, render again
+    with Renderer(flat) as r:
+        got, got8, stats = r.render(cam, family="wavefront", precision=precision)
+    assert np.array_equal(got.view(bits), want.view(bits)) and np.array_equal(got8, want8)
+    assert {k: stats[k] for k in COUNTERS} == {k: wstats[k] for k in COUNTERS}
