@@ -309,7 +309,7 @@ CALIBRATION_FRAMES = 4  # 2 per kernel family (TUNE_RUNS in csrc/rtgpu.cu)
 
 
 PROFILED_TRAFFIC = {  # (scene, width, height, precision, depth, family) -> committed ncu per-launch list of one frame
-    ("cover", 1920, 1080, "f64", 6, "wavefront"): "profiles/r2b_wavefront_launches.csv",
+    ("cover", 1920, 1080, "f64", 6, "wavefront"): "profiles/r2c_wavefront_launches.csv",
     ("synthetic:100000", 7680, 4320, "f64", 6, "wavefront"): "profiles/r2_synthetic_1e5_8k_launches.csv",
 }
 
@@ -342,10 +342,6 @@ def hbm_peak_gbs():
         return 6550.0, "B200_PROFILING.md fallback (measured copy bandwidth of this pool's B200s)"
 
 
-def launches_per_frame(family: str, max_depth: int) -> int:
-    """Kernels of this library per frame: the persistent family is one launch; the wavefront family is a level
-    kernel and a combine kernel per recursion level and one counter commit."""
-    return 1 if family == "persistent" else 2 * (max_depth + 1) + 1
 
 
 def run_b200(args):
@@ -424,6 +420,7 @@ def run_b200(args):
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     with ClockSampler(local_rank) as clocks:
         barrier()
+        launches0 = renderer.launch_count()
         t_wall0 = time.perf_counter()
         for i in range(K):
             flush.fill_(i & 0xFF)  # L2 flush between timed steps (outside the event pair)
@@ -432,9 +429,11 @@ def run_b200(args):
             ends[i].record(stream)
         barrier()
         t_wall1 = time.perf_counter()
+        launches_timed = renderer.launch_count() - launches0  # counted by the library at every kernel launch site
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     family_used = last_family()
     device_ms = max_over_ranks(sum(step_ms))
+    gpu_launches = int(sum_over_ranks([float(launches_timed)])[0])
     counters = [int(v) // K for v in sum_over_ranks([float(v) for v in d_counters.tolist()])]
     stats = dict(zip(("rays_primary", "rays_shadow", "rays_reflect", "rays_refract", "hit_nodes", "pixels"), counters))
     rays = stats["rays_primary"] + stats["rays_shadow"] + stats["rays_reflect"] + stats["rays_refract"]
@@ -524,6 +523,7 @@ def run_b200(args):
         # in-run model of the same traffic: every queued hit is one ray record written and read once, every node record
         # is written once and read once by the combine pass, every child colour is one 24-byte slot write, and the
         # frame is written once (counts from this run's device counters; record sizes from the library)
+        # (a binned frame also moves 24 bytes of keys and permutation per queued hit; the model leaves them out)
         traffic_model = (2.0 * records["queued_rays"] * records["ray_record_bytes"] + 2.0 * records["node_records"] * records["node_record_bytes"] +
                          records["queued_rays"] * 3.0 * elem + n_px * 3.0 * elem)
         hbm_peak, hbm_peak_source = hbm_peak_gbs()
@@ -531,11 +531,15 @@ def run_b200(args):
         roofline = {
             "bound": "fp64_fma_pipe" if args.precision == "f64" else "fp32_fma_pipe", "achieved": achieved, "peak": peak_tflops,
             "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": traffic, "traffic_source": traffic_source,
-            "kernel": "rt::wf_level_kernel x (max_depth + 1) = 90 % of the step (profiles/r2_wavefront_launches.md); achieved = "
+            "kernel": "rt::wf_level_kernel x (max_depth + 1) = 87 % of the step (profiles/r2c_wavefront_launches.md); achieved = "
                       "frame flops / frame time" if family_used == "wavefront" else "rt::render_kernel (the whole step)",
             "peak_source": "measured live: 8 independent FMA chains per thread on every SM (rtgpu_measure_fma_peak); "
                            "MEASURED_PEAKS.json holds only HBM and bf16 peaks",
             "algorithmic_flops_per_frame": flops, "flops_per_ray": flops_per_ray(flat),
+            "frac_note": "frac = the reference's brute-force flops (every shape tested exactly for every ray, SURVEY 8d) / time / peak: the "
+                         "kernels skip most of those tests with a single-precision bounding-sphere pre-test, so frac is a speed relative to a "
+                         "brute-force machine at peak, not pipe occupancy (profiled FP64 pipe: 26-31 % busy, issue slots 63-73 %, "
+                         "profiles/r2c_wavefront_launches.md)",
             "traffic_model": traffic_model, "traffic_model_source": "in-run: device record counts (rtgpu_context_frame_records) x record sizes + the frame write",
             "hbm": {"achieved_gbs": (traffic or traffic_model) / (device_ms / K * 1e-3) / 1e9 / world, "peak_gbs": hbm_peak, "peak_source": hbm_peak_source,
                     "frac": (traffic or traffic_model) / (device_ms / K * 1e-3) / 1e9 / world / hbm_peak,
@@ -594,7 +598,7 @@ def run_b200(args):
             "family": family_used, "family_requested": args.family,
             "family_calibration_frames": CALIBRATION_FRAMES if family is None else 0,
             "frame": frame_id, "cold_one_shot": cold,
-            "e2e": e2e, "gpu_launches": launches_per_frame(family_used, args.max_depth) * K * world, "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_summary,
+            "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clock_summary,
             "rays_per_frame": rays, "ms_per_frame": device_ms / K, "wall_ms_per_step_incl_flush": (t_wall1 - t_wall0) * 1e3 / K,
             "counters": stats,
         }

@@ -250,6 +250,11 @@ int rtgpu_last_family(void);
  * record.  Benchmarks turn this into the frame's algorithmic queue traffic without a profiler. */
 int rtgpu_context_frame_records(rtgpu_context *context, uint64_t out[4]);
 
+/* Render kernels this library has launched for the context since it was created (level / bin / combine / commit /
+ * status kernels of the wavefront family, one launch per frame of the persistent family).  Benchmarks report the
+ * difference across their timed region as the number of kernels that ran in it. */
+uint64_t rtgpu_context_launch_count(rtgpu_context *context);
+
 /* -- pinned host memory ---------------------------------------------------------------------- */
 /* Page-locked, device-mapped host memory.  When out_rgb / out_rgb8 of a host-buffer render live in such
  * memory (these functions, cudaHostAlloc, cudaHostRegister, torch pin_memory ...) the persistent kernel writes

@@ -160,6 +160,7 @@ unsafe extern "C" {
     ) -> c_int;
     pub fn rtgpu_last_family() -> c_int;
     pub fn rtgpu_context_frame_records(context: *mut rtgpu_context, out: *mut u64) -> c_int;
+    pub fn rtgpu_context_launch_count(context: *mut rtgpu_context) -> u64;
     pub fn rtgpu_host_alloc(bytes: usize) -> *mut c_void;
     pub fn rtgpu_host_free(ptr: *mut c_void);
     pub fn rtgpu_measure_fma_peak(device: c_int, precision: u32, out_tflops: *mut f64, out_ms: *mut f64) -> c_int;

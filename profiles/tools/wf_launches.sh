@@ -1,9 +1,10 @@
 #!/bin/bash
 # Per-launch metrics of the wavefront family for one frame (after the same command exited 0 without ncu).
+# A binned frame is 7 level + 6 bin + 7 combine + 1 commit = 21 launches (WF_SKIP / WF_COUNT: 60 / 15 for an unbinned one).
 mkdir -p gpurun_out
 python bench.py --family wavefront --steps 2 --warmup 3 "$@" > gpurun_out/plain_wf.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__icc_request_hit_rate.pct,gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed,sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,sm__cycles_active.avg,sm__cycles_elapsed.avg,smsp__warps_active.avg.per_cycle_active,smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio,smsp__average_warps_issue_stalled_wait_per_issue_active.ratio,smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio,smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio,smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio,smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio,smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio,smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio \
-  --clock-control none -k regex:"wf_" -s 60 -c 15 --csv --log-file gpurun_out/wf_launches.csv python bench.py --family wavefront --steps 2 --warmup 3 "$@" > gpurun_out/ncu_wf.log 2>&1
+  --clock-control none -k regex:"wf_" -s ${WF_SKIP:-62} -c ${WF_COUNT:-21} --csv --log-file gpurun_out/wf_launches.csv python bench.py --family wavefront --steps 2 --warmup 3 "$@" > gpurun_out/ncu_wf.log 2>&1
 python - <<'PY'
 import csv, collections
 rows=[r for r in csv.reader(open("gpurun_out/wf_launches.csv")) if len(r)>10]

@@ -23,7 +23,7 @@ def f(v, k):
 
 
 def short(n):
-    for k in ("wf_level_kernel", "wf_combine_kernel", "wf_commit_counters_kernel"):
+    for k in ("wf_level_kernel", "wf_combine_kernel", "wf_commit_counters_kernel", "wf_bin_kernel"):
         if k in n:
             return k
     return n[:30]
@@ -47,7 +47,7 @@ for i, (k, v) in enumerate(per.items()):
           f"{g('smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio')} | "
           f"{g('smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio')} |")
 share = lambda sub: 100 * sum(f(v, "gpu__time_duration.sum") for v in per.values() if sub in v["name"]) / tot  # noqa: E731
-print("\nLevel kernels: %.1f %% of the frame; combine kernels %.1f %%; counter commit %.1f %%." % (share("wf_level"), share("combine"), share("commit")))
+print("\nLevel kernels: %.1f %% of the frame; combine kernels %.1f %%; bin kernels %.1f %%; counter commit %.1f %%." % (share("wf_level"), share("combine"), share("wf_bin"), share("commit")))
 print("DRAM per frame: %.0f MB written, %.0f MB read (bench.py reports the sum as `roofline.traffic`)." % (
     sum(f(v, "dram__bytes_write.sum") for v in per.values()) / 1e6, sum(f(v, "dram__bytes_read.sum") for v in per.values()) / 1e6))
 reading = {
@@ -62,6 +62,11 @@ level-0 launch): with the node state parked in shared memory the level kernels r
 instruction counts and threads per instruction are those of round 1 — the divergence of the exact tests at depth
 (17.6-25 threads per instruction at levels 1-6) is unchanged and is what is left.  The combine kernels (9.6 % of the
 frame) are memory-latency bound at ~3.8 TB/s.""",
+    "r2c_wavefront_launches.csv": """
+Reading (end of round 2: single-precision pre-test, binned queues): a level's queue is consumed grouped by (hit shape,
+reflected / refracted), which lifts the deeper levels from 17.9-25.3 to **21.9-29.3 threads per instruction**; the
+pre-test no longer touches the FP64 pipe (26-31 % busy instead of 47-52 %: what is left there are the exact tests), issue
+slots 63-73 % busy.  The six bin kernels (one pass over the (bin, rank) keys of a queue each) cost 7 µs apiece.""",
     "r2_synthetic_1e5_8k_launches.csv": """
 Reading: the BVH path.  Level 0 is 70 % of the frame at 18.7 threads per instruction; the deeper levels run at 6-9.
 After moving the box tests to single precision the FP64 pipe is 2-4 % busy (only the exact leaf tests use it) and the

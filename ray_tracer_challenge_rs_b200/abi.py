@@ -135,6 +135,7 @@ EXPORTED_SYMBOLS = (
     "rtgpu_context_render",
     "rtgpu_last_family",
     "rtgpu_context_frame_records",
+    "rtgpu_context_launch_count",
     "rtgpu_host_alloc",
     "rtgpu_host_free",
     "rtgpu_measure_fma_peak",
@@ -219,6 +220,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.rtgpu_measure_fma_peak.argtypes = [C.c_int, C.c_uint32, _pd, _pd]
     lib.rtgpu_context_frame_records.restype = C.c_int
     lib.rtgpu_context_frame_records.argtypes = [C.c_void_p, _pu64]
+    lib.rtgpu_context_launch_count.restype = C.c_uint64
+    lib.rtgpu_context_launch_count.argtypes = [C.c_void_p]
     lib.rtgpu_last_family.restype = C.c_int
     lib.rtgpu_last_family.argtypes = []
     lib.rtgpu_host_alloc.restype = C.c_void_p

@@ -652,6 +652,7 @@ struct rtgpu_context {
     unsigned long long* d_wf_keys = nullptr;  // binned queues (rt_wavefront.cuh wf_bin_kernel): (bin, rank) per queue entry ...
     unsigned* d_wf_perm = nullptr;            // ... and the permutation the next level consumes its queue through
     size_t wf_bin_entries = 0;                // entries both arrays hold
+    uint64_t launches = 0;                    // kernels launched for this context so far (rtgpu_context_launch_count)
     size_t wf_cap_rays = 0, wf_cap_nodes = 0;  // in elements
     size_t wf_bytes_rays = 0, wf_bytes_nodes = 0;
     bool wf_used = false;  // the last launch took the wavefront path (overflow must be checked after it)
@@ -718,6 +719,7 @@ int launch_kernel_impl(rtgpu_context* ctx, const T* d_reals, const rt::CameraPar
     if (grid < 1) grid = 1;
     CUDA_TRY(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned int), stream));
     kernel<<<(unsigned)grid, RT_BLOCK_THREADS, smem, stream>>>(d_reals, ctx->d_ints, lay, cam, d_out, d_out8, d_counters, ctx->d_work);
+    ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return RTGPU_OK;
 }
@@ -978,8 +980,11 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
                                                             (binned && level > 0) ? ctx->d_wf_perm : nullptr,
                                                             (binned && level + 1 < levels) ? ctx->d_wf_keys : nullptr);
         CUDA_TRY(cudaGetLastError());
-        if (binned && level + 1 < levels)
+        ctx->launches++;
+        if (binned && level + 1 < levels) {
             rt::wf_bin_kernel<<<ctx->sm_count * 4, 256, 0, stream>>>(ctx->d_wf_counts, level + 1, (unsigned)ctx->wf_cap_rays, ctx->d_wf_keys, ctx->d_wf_perm);
+            ctx->launches++;
+        }
         if (debug_sync) {
             const double t0 = wall_ms();
             CUDA_TRY(cudaStreamSynchronize(stream));
@@ -991,6 +996,7 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
     }
     for (int level = levels - 1; level >= 0; --level)
         rt::wf_combine_kernel<T><<<ctx->sm_count * 4, 256, 0, stream>>>(nodes, ctx->d_wf_counts, level, (unsigned)ctx->wf_cap_nodes, d_out, d_out8);
+    ctx->launches += (uint64_t)levels;
     CUDA_TRY(cudaGetLastError());
     ctx->wf_used = true;
     return RTGPU_OK;
@@ -1023,6 +1029,7 @@ int wavefront_check(rtgpu_context* ctx, uint64_t pixels, cudaStream_t stream, bo
     if (!published || !ctx->h_status->valid) {
         ctx->h_status->valid = 0u;
         publish_status_kernel<<<1, 32, 0, stream>>>(nullptr, ctx->d_wf_counts, ctx->d_status);
+        ctx->launches++;
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaStreamSynchronize(stream));
     }
@@ -1112,13 +1119,19 @@ int render_wavefront(rtgpu_context* ctx, const T* d_reals, const rt::CameraParam
         int st = launch_wavefront<T>(ctx, d_reals, cam, d_out, d_out8, counters, stream);
         if (st != RTGPU_OK) return st;
         if (!blocking) {
-            if (counters) wf_commit_counters_kernel<<<1, 32, 0, stream>>>(ctx->d_wf_priv, counters);
+            if (counters) {
+                wf_commit_counters_kernel<<<1, 32, 0, stream>>>(ctx->d_wf_priv, counters);
+                ctx->launches++;
+            }
             return RTGPU_OK;
         }
         st = wavefront_check<T>(ctx, pixels, stream);
         if (st < 0) return st;
         if (st == 0) {
-            if (counters) wf_commit_counters_kernel<<<1, 32, 0, stream>>>(ctx->d_wf_priv, counters);
+            if (counters) {
+                wf_commit_counters_kernel<<<1, 32, 0, stream>>>(ctx->d_wf_priv, counters);
+                ctx->launches++;
+            }
             CUDA_TRY(cudaGetLastError());
             return RTGPU_OK;
         }
@@ -1283,6 +1296,7 @@ void* mapped_device_pointer(const void* host) {
 int publish_status(rtgpu_context* ctx) {
     ctx->h_status->valid = 0u;
     publish_status_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_counters, ctx->wf_used ? ctx->d_wf_counts : nullptr, ctx->d_status);
+    ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return RTGPU_OK;
 }
@@ -1762,6 +1776,8 @@ int rtgpu_context_render_device(rtgpu_context* context, const rtgpu_camera* came
 }
 
 int rtgpu_last_family(void) { return g_last_family; }
+
+uint64_t rtgpu_context_launch_count(rtgpu_context* context) { return context ? context->launches : 0u; }
 
 int rtgpu_context_frame_records(rtgpu_context* context, uint64_t out[4]) {
     if (!context || !out) return fail(RTGPU_ERR_INVALID_ARGUMENT, "context or out is NULL");

@@ -175,6 +175,10 @@ class Renderer:
         abi.check(self._lib, st)
         return out_rgb, out_rgb8, dict(stats.as_dict(), family=last_family())
 
+    def launch_count(self) -> int:
+        """Render kernels launched for this context so far (``rtgpu_context_launch_count``)."""
+        return int(self._lib.rtgpu_context_launch_count(self._ctx))
+
     def frame_records(self) -> dict:
         """What the wavefront family moved through HBM for the most recent host-buffer frame (``rtgpu_context_frame_records``)."""
         out = (C.c_uint64 * 4)()

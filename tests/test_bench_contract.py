@@ -10,7 +10,6 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from bench import launches_per_frame  # noqa: E402
 
 BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
              "dtype", "data", "config", "e2e", "cpu_baseline"}
@@ -59,7 +58,10 @@ def test_b200_arm_line_has_the_contract_keys():
     assert line["n_gpus"] == 1 and line["steps"] == 3 and line["dtype"] == "f64" and line["vs_baseline"] is None
     assert line["family"] in ("persistent", "wavefront")
     assert set(line["config"]) == {"workload", "scene", "width", "height", "precision", "max_depth", "shapes", "lights", "cache"}  # = the reference arm's
-    assert line["gpu_launches"] == 3 * launches_per_frame(line["family"], 6)
+    # counted by the library (rtgpu_context_launch_count): one kernel per frame of the persistent family; a level and a
+    # combine kernel per recursion level, the status block and the counter commit for the wavefront family (no bin
+    # kernels at this size)
+    assert line["gpu_launches"] == 3 * {"persistent": 1, "wavefront": 2 * 7 + 2}[line["family"]]
     # pixel identity the driver can read: both legs' frames equal a 1-GPU render, and their RGB8 equals the oracle's
     assert line["frame"]["frame_matches_n1"] is True and len(line["frame"]["frame_sha256"]) == 64
     assert line["frame"]["rgb8_pixels_differing_from_oracle"] == 0
