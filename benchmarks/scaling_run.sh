@@ -1,6 +1,6 @@
 #!/bin/bash
 # Both bench arms at N GPUs of one box, for cover@1080p (BASELINE configs[1]) and the synthetic 1e5-shape scene at 8K
-# (configs[4]); results under gpurun_out/.   benchmarks/scaling_run.sh <N> [tag]
+# (configs[4]; SKIP_SYN=1 leaves it out); results under gpurun_out/.   benchmarks/scaling_run.sh <N> [tag]
 N=$1; TAG=${2:-r2}
 run() {  # run <outfile> <bench args...>
   out=$1; shift
@@ -11,7 +11,7 @@ run() {  # run <outfile> <bench args...>
 mkdir -p gpurun_out
 run scale_${TAG}_ref_n$N --impl reference --steps 2 --warmup 1
 run scale_${TAG}_n$N --steps 20 --warmup 3 --no-cold
-run scale_${TAG}_syn1e5_n$N --scene synthetic:100000 --width 7680 --height 4320 --steps 5 --warmup 3 --no-cold
+[ -n "$SKIP_SYN" ] || run scale_${TAG}_syn1e5_n$N --scene synthetic:100000 --width 7680 --height 4320 --steps 5 --warmup 3 --no-cold
 python - <<PY
 import json
 for name in ("scale_${TAG}_ref_n$N", "scale_${TAG}_n$N", "scale_${TAG}_syn1e5_n$N"):
