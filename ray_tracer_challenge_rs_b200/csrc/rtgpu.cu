@@ -872,6 +872,9 @@ constexpr double WF_RAYS_PER_PIXEL = 1.0, WF_NODES_PER_PIXEL = 2.0;
 // of the shapes reflective or transparent (cover 18 of 19: -4.4 %; reflect_refract 7 of 13: -2.5 %; table 6 of 18: +-0;
 // cylinders 3 of 11: +5 %), at least 8 shapes (scenes of 3-6 shapes: +6..8 % when forced on) and 2^18 pixels per launch
 // (smaller launches are bound by launch latency); everything else stays in arrival order.  profiles/r2_notes.md.
+#ifndef RT_WF_COMBINE_CTAS
+#define RT_WF_COMBINE_CTAS 8  // CTAs of 256 threads per SM in the combine pass (full occupancy)
+#endif
 constexpr uint64_t WF_BIN_MIN_PIXELS = 1u << 18;
 constexpr uint32_t WF_BIN_MIN_SHAPES = 8;
 
@@ -995,7 +998,7 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
         }
     }
     for (int level = levels - 1; level >= 0; --level)
-        rt::wf_combine_kernel<T><<<ctx->sm_count * 4, 256, 0, stream>>>(nodes, ctx->d_wf_counts, level, (unsigned)ctx->wf_cap_nodes, d_out, d_out8);
+        rt::wf_combine_kernel<T><<<ctx->sm_count * RT_WF_COMBINE_CTAS, 256, 0, stream>>>(nodes, ctx->d_wf_counts, level, (unsigned)ctx->wf_cap_nodes, d_out, d_out8);
     ctx->launches += (uint64_t)levels;
     CUDA_TRY(cudaGetLastError());
     ctx->wf_used = true;
