@@ -53,6 +53,14 @@ namespace rt {
 #ifndef RT_CULL
 #define RT_CULL 1  // bounding-sphere pre-test in the intersection loop (exact results either way)
 #endif
+#ifndef RT_BOUNDS_CHECK
+#define RT_BOUNDS_CHECK 0  // 1: every table / queue / node / permutation index is range-checked on the device; a bad one traps
+#endif
+#if RT_BOUNDS_CHECK
+#define RT_CHECK(cond) do { if (!(cond)) { printf("rtgpu bounds check failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); __trap(); } } while (0)
+#else
+#define RT_CHECK(cond) do { } while (0)
+#endif
 #ifndef RT_CULL_F32
 #define RT_CULL_F32 1  // f64 kernels: the pre-test runs in single precision with proven margins (trace_unified); exact results either way
 #endif
@@ -229,19 +237,19 @@ struct SceneView {
             return rt_scene_smem;
         }
     }
-    RT_DEV const T* shape(uint32_t pos) const { return R() + (size_t)pos * SHAPE_REALS; }
-    RT_DEV int4 shape_meta(uint32_t pos) const { return reinterpret_cast<const int4*>(I())[(size_t)pos * (SHAPE_INTS / 4)]; }
+    RT_DEV const T* shape(uint32_t pos) const { RT_CHECK(pos < L.n_shapes); return R() + (size_t)pos * SHAPE_REALS; }
+    RT_DEV int4 shape_meta(uint32_t pos) const { RT_CHECK(pos < L.n_shapes); return reinterpret_cast<const int4*>(I())[(size_t)pos * (SHAPE_INTS / 4)]; }
     RT_DEV const T* triangle(uint32_t pos) const { return R() + L.tri_off + (size_t)I()[(size_t)pos * SHAPE_INTS + 4] * TRI_REALS; }
-    RT_DEV const T* bvh_boxes(uint32_t node) const { return R() + L.bvh_off + (size_t)node * BVH_REALS; }
-    RT_DEV const float4* bvh_node32(uint32_t node) const { return reinterpret_cast<const float4*>(I() + L.bvh32_off) + (size_t)node * (BVH32_WORDS / 4); }
-    RT_DEV int2 bvh_children(uint32_t node) const { return reinterpret_cast<const int2*>(I() + L.bvh_meta_off)[node]; }
-    RT_DEV const T* material(uint32_t m) const { return R() + L.mat_off + (size_t)m * MAT_REALS; }
-    RT_DEV int material_pattern(uint32_t m) const { return I()[L.mat_meta_off + m * MAT_INTS]; }
-    RT_DEV const T* pattern(uint32_t p) const { return R() + L.pat_off + (size_t)p * PAT_REALS; }
-    RT_DEV const int* pattern_meta(uint32_t p) const { return I() + L.pat_meta_off + p * PAT_INTS; }
-    RT_DEV const T* light(uint32_t l) const { return R() + L.light_off + (size_t)l * LIGHT_REALS; }
-    RT_DEV const T* cull(uint32_t pos) const { return R() + L.cull_off + (size_t)pos * CULL_REALS; }
-    RT_DEV const float4* cull32(uint32_t pos) const { return reinterpret_cast<const float4*>(I() + L.cull32_off) + pos; }
+    RT_DEV const T* bvh_boxes(uint32_t node) const { RT_CHECK(node < L.n_bvh_nodes); return R() + L.bvh_off + (size_t)node * BVH_REALS; }
+    RT_DEV const float4* bvh_node32(uint32_t node) const { RT_CHECK(node < L.n_bvh_nodes); return reinterpret_cast<const float4*>(I() + L.bvh32_off) + (size_t)node * (BVH32_WORDS / 4); }
+    RT_DEV int2 bvh_children(uint32_t node) const { RT_CHECK(node < L.n_bvh_nodes); return reinterpret_cast<const int2*>(I() + L.bvh_meta_off)[node]; }
+    RT_DEV const T* material(uint32_t m) const { RT_CHECK(m < L.n_materials); return R() + L.mat_off + (size_t)m * MAT_REALS; }
+    RT_DEV int material_pattern(uint32_t m) const { RT_CHECK(m < L.n_materials); return I()[L.mat_meta_off + m * MAT_INTS]; }
+    RT_DEV const T* pattern(uint32_t p) const { RT_CHECK(p < L.n_patterns); return R() + L.pat_off + (size_t)p * PAT_REALS; }
+    RT_DEV const int* pattern_meta(uint32_t p) const { RT_CHECK(p < L.n_patterns); return I() + L.pat_meta_off + p * PAT_INTS; }
+    RT_DEV const T* light(uint32_t l) const { RT_CHECK(l < L.n_lights); return R() + L.light_off + (size_t)l * LIGHT_REALS; }
+    RT_DEV const T* cull(uint32_t pos) const { RT_CHECK(pos <= L.n_shapes); return R() + L.cull_off + (size_t)pos * CULL_REALS; }
+    RT_DEV const float4* cull32(uint32_t pos) const { RT_CHECK(pos <= L.n_shapes); return reinterpret_cast<const float4*>(I() + L.cull32_off) + pos; }
     RT_DEV T cull_shrink() const { return sizeof(T) == 8 ? (T)L.cull_shrink64 : (T)L.cull_shrink32; }
 };
 

@@ -249,7 +249,9 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
         } else if (active && (item < n_front || item >= front_padded)) {
             // the parent's launch already traced this ray and only queued it because it hit
             q_index = item < n_front ? item : cap_rays - 1u - (item - front_padded);
+            RT_CHECK(q_index < cap_rays);
             if (perm_in) q_index = perm_in[q_index];
+            RT_CHECK(q_index < cap_rays);
             const WfRay<T>& r = rays_in[q_index];
             PK(PK_P + 0) = r.ox; PK(PK_P + 1) = r.oy; PK(PK_P + 2) = r.oz;
             PK(PK_D + 0) = r.dx; PK(PK_D + 1) = r.dy; PK(PK_D + 2) = r.dz;
@@ -443,6 +445,7 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                             r.parent = (int)node_index;
                             r.slot = child;
                             r.pad = 0;
+                            RT_CHECK(q < cap_rays && r.pos >= 0 && (uint32_t)r.pos < sv.L.n_shapes && r.parent >= 0 && (unsigned)r.parent < cap_nodes);
                             rays_out[q] = r;
                             if (keys_out) keys_out[q] = ((unsigned long long)bin << 32) | rank;
                         } else {
@@ -484,6 +487,7 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
                     nd.surface[0] = surface.x; nd.surface[1] = surface.y; nd.surface[2] = surface.z;
                     nd.reflected[0] = nd.reflected[1] = nd.reflected[2] = T(0);  // world.rs:121
                     nd.refracted[0] = nd.refracted[1] = nd.refracted[2] = T(0);  // world.rs:137,146
+                    RT_CHECK(node_index < cap_nodes && (parent < 0 || (unsigned)parent < cap_nodes));
                     nodes[node_index] = nd;
                 } else if (alive) {
                     // world.rs:59-66 with black children: (surface + 0) + 0 — and 0 * reflectance is 0 too — is `surface`
@@ -571,6 +575,7 @@ RT_DEV void wf_combine_node(WfNode<T>* __restrict__ nodes, const WfNode<T>& n, T
         wf_store_pixel(out_rgb, out_rgb8, (size_t)(unsigned)~n.link, colour);  // Camera::render_parallel, camera.rs:108
     } else {
         const V3<T> c = colour * n.k_parent;  // world.rs:127 / 156
+        RT_CHECK(n.link >= 0);
         T* dst = (n.slot_flags & 1) == 0 ? nodes[n.link].reflected : nodes[n.link].refracted;
         dst[0] = c.x; dst[1] = c.y; dst[2] = c.z;
     }
@@ -628,6 +633,7 @@ __global__ void __launch_bounds__(256) wf_bin_kernel(const WfCounts* __restrict_
             }
             const bool back = i0 + (unsigned)u * stride >= n_front;
             const unsigned s = base[back ? 1 : 0][(unsigned)(key[u] >> 32) & (RT_WF_BINS - 1)] + (unsigned)key[u];
+            RT_CHECK(q[u] < cap_rays && s < (back ? n_back : n_front));
             if (s < (back ? n_back : n_front)) perm[back ? cap_rays - 1u - s : s] = q[u];
         }
     }
