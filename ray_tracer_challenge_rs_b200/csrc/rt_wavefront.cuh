@@ -85,6 +85,10 @@ struct WfCounts {
     unsigned overflow;         // a queue or the node array was too small: the frame must be re-rendered
 };
 
+// Programmatic dependent launch, device side (sm_90+; both are no-ops for a kernel launched the ordinary way).
+RT_DEV void wf_release_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+RT_DEV void wf_wait_for_previous() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 #ifndef RT_WF_SYNC
 #define RT_WF_SYNC 0
 #endif
@@ -159,6 +163,12 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t tiles_x = (cam.hsize + TILE_W - 1) / TILE_W;
     const uint32_t tiles_y = (cam.n_rows + TILE_H - 1) / TILE_H;
+    // Programmatic dependent launch (rtgpu.cu launch_chain): the next kernel of the frame may be scheduled as soon as
+    // this grid's CTAs leave the SMs; it stages its scene tables while our tail is still running and then waits, as we do
+    // here, for the previous grid to have completed and flushed before it touches anything that grid wrote.
+    wf_release_dependents();
+    if constexpr (SMEM) stage_scene<T>(layout, g_reals, g_ints);  // reads only the scene blobs: before the wait
+    wf_wait_for_previous();
     // level > 0: front entries, padding to a warp boundary, then back entries
     unsigned n_front = 0, n_back = 0;
     if (level > 0) {
@@ -179,9 +189,6 @@ wf_level_kernel(const T* __restrict__ g_reals, const int* __restrict__ g_ints, S
     unsigned* const my_count = s_count[threadIdx.x >> 5];
     if (lane < 4u) my_count[lane] = 0u;
     __syncwarp();
-    if constexpr (SMEM) {
-        if (n_items) stage_scene<T>(layout, g_reals, g_ints);  // (uniform over the grid) nothing queued: nothing to stage
-    }
     // behind the staged tables: the warps' scratch for the pair-list trace (if compiled in), then WF_PARK_REALS columns
     // of per-thread node state
     PairScratch<T>* const ws = reinterpret_cast<PairScratch<T>*>(sv.scratch()) + (threadIdx.x >> 5);
@@ -590,6 +597,8 @@ __global__ void __launch_bounds__(256) wf_bin_kernel(const WfCounts* __restrict_
     static_assert(RT_WF_BINS == 64, "the scan below is written for two warps per end");
     __shared__ unsigned base[2][RT_WF_BINS];
     __shared__ unsigned warp_total[4];
+    wf_release_dependents();
+    wf_wait_for_previous();
     unsigned n_front = counts->n_rays[level], n_back = counts->n_back[level];
     const bool overflowed = (unsigned long long)n_front + n_back > cap_rays;
     if (overflowed) {
@@ -642,6 +651,8 @@ __global__ void __launch_bounds__(256) wf_bin_kernel(const WfCounts* __restrict_
 template <typename T>
 __global__ void wf_combine_kernel(WfNode<T>* __restrict__ nodes, const WfCounts* __restrict__ counts, int level, unsigned cap_nodes,
                                   T* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8) {
+    wf_release_dependents();
+    wf_wait_for_previous();
     const unsigned begin = level == 0 ? 0u : min(counts->node_end[level - 1], cap_nodes);
     const unsigned end = min(counts->node_end[level], cap_nodes);
     const unsigned stride = gridDim.x * blockDim.x;

@@ -731,11 +731,14 @@ int launch_kernel_impl(rtgpu_context* ctx, const T* d_reals, const rt::CameraPar
 #endif
 
 __global__ void wf_commit_counters_kernel(const unsigned long long* priv, unsigned long long* user) {
+    rt::wf_release_dependents();
+    rt::wf_wait_for_previous();
     if (threadIdx.x < rt::NUM_COUNTERS && priv[threadIdx.x]) atomicAdd(&user[threadIdx.x], priv[threadIdx.x]);
 }
 
 // Last kernel of a host-buffer frame: everything the host wants to know, written into mapped pinned memory.
 __global__ void publish_status_kernel(const unsigned long long* counters, const rt::WfCounts* wf, rtgpu_context::HostStatus* out) {
+    rt::wf_wait_for_previous();
     if (threadIdx.x < rt::NUM_COUNTERS) out->counters[threadIdx.x] = counters ? counters[threadIdx.x] : 0ull;
     if (threadIdx.x == 0) {
         unsigned max_rays = 0;
@@ -920,6 +923,26 @@ int wavefront_reserve(rtgpu_context* ctx, uint64_t pixels, double growth) {
 
 double wall_ms();
 
+// One kernel of a frame's chain.  dependent: launched with programmatic stream serialization — it may start while the
+// previous kernel of the stream is still draining; every kernel of the chain waits (griddepcontrol.wait) before it
+// reads what its predecessor wrote, and releases its own successor at once (rt_wavefront.cuh wf_release_dependents).
+// RTGPU_PDL=0 launches everything the ordinary way.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chain(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream, bool dependent, Args&&... args) {
+    static const bool allowed = !(getenv("RTGPU_PDL") && getenv("RTGPU_PDL")[0] == '0');
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (dependent && allowed) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
 template <typename T, bool FULL, bool BVH, bool SMEM>
 int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::CameraParams<T>& cam, T* d_out, uint8_t* d_out8,
                           unsigned long long* d_counters, cudaStream_t stream) {
@@ -978,14 +1001,15 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
     for (int level = 0; level < levels; ++level) {
         const rt::WfRay<T>* in = reinterpret_cast<const rt::WfRay<T>*>(ctx->d_wf_rays[level & 1]);
         rt::WfRay<T>* out = reinterpret_cast<rt::WfRay<T>*>(ctx->d_wf_rays[(level + 1) & 1]);
-        level_kernel<<<grid, RT_WF_THREADS, smem, stream>>>(d_reals, ctx->d_ints, lay, cam, level, in, out, (unsigned)ctx->wf_cap_rays, nodes,
-                                                            (unsigned)ctx->wf_cap_nodes, ctx->d_wf_counts, d_out, d_out8, ctx->d_wf_priv,
-                                                            (binned && level > 0) ? ctx->d_wf_perm : nullptr,
-                                                            (binned && level + 1 < levels) ? ctx->d_wf_keys : nullptr);
-        CUDA_TRY(cudaGetLastError());
+        // level 0 follows the frame's memsets (an ordinary dependency); everything after it is chained
+        CUDA_TRY(launch_chain(level_kernel, grid, RT_WF_THREADS, smem, stream, level > 0, d_reals, (const int*)ctx->d_ints, lay, cam, level, in, out,
+                              (unsigned)ctx->wf_cap_rays, nodes, (unsigned)ctx->wf_cap_nodes, ctx->d_wf_counts, d_out, d_out8, ctx->d_wf_priv,
+                              (const unsigned*)((binned && level > 0) ? ctx->d_wf_perm : nullptr),
+                              (unsigned long long*)((binned && level + 1 < levels) ? ctx->d_wf_keys : nullptr)));
         ctx->launches++;
         if (binned && level + 1 < levels) {
-            rt::wf_bin_kernel<<<ctx->sm_count * 4, 256, 0, stream>>>(ctx->d_wf_counts, level + 1, (unsigned)ctx->wf_cap_rays, ctx->d_wf_keys, ctx->d_wf_perm);
+            CUDA_TRY(launch_chain(rt::wf_bin_kernel, (unsigned)ctx->sm_count * 4u, 256u, 0, stream, true, (const rt::WfCounts*)ctx->d_wf_counts, level + 1,
+                                  (unsigned)ctx->wf_cap_rays, (const unsigned long long*)ctx->d_wf_keys, ctx->d_wf_perm));
             ctx->launches++;
         }
         if (debug_sync) {
@@ -998,7 +1022,8 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
         }
     }
     for (int level = levels - 1; level >= 0; --level)
-        rt::wf_combine_kernel<T><<<ctx->sm_count * RT_WF_COMBINE_CTAS, 256, 0, stream>>>(nodes, ctx->d_wf_counts, level, (unsigned)ctx->wf_cap_nodes, d_out, d_out8);
+        CUDA_TRY(launch_chain(rt::wf_combine_kernel<T>, (unsigned)ctx->sm_count * RT_WF_COMBINE_CTAS, 256u, 0, stream, !debug_sync, nodes,
+                              (const rt::WfCounts*)ctx->d_wf_counts, level, (unsigned)ctx->wf_cap_nodes, d_out, d_out8));
     ctx->launches += (uint64_t)levels;
     CUDA_TRY(cudaGetLastError());
     ctx->wf_used = true;
@@ -1031,7 +1056,7 @@ int wavefront_check(rtgpu_context* ctx, uint64_t pixels, cudaStream_t stream, bo
     ctx->wf_used = false;
     if (!published || !ctx->h_status->valid) {
         ctx->h_status->valid = 0u;
-        publish_status_kernel<<<1, 32, 0, stream>>>(nullptr, ctx->d_wf_counts, ctx->d_status);
+        CUDA_TRY(launch_chain(publish_status_kernel, 1u, 32u, 0, stream, true, (const unsigned long long*)nullptr, (const rt::WfCounts*)ctx->d_wf_counts, ctx->d_status));
         ctx->launches++;
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaStreamSynchronize(stream));
@@ -1123,7 +1148,7 @@ int render_wavefront(rtgpu_context* ctx, const T* d_reals, const rt::CameraParam
         if (st != RTGPU_OK) return st;
         if (!blocking) {
             if (counters) {
-                wf_commit_counters_kernel<<<1, 32, 0, stream>>>(ctx->d_wf_priv, counters);
+                CUDA_TRY(launch_chain(wf_commit_counters_kernel, 1u, 32u, 0, stream, true, (const unsigned long long*)ctx->d_wf_priv, counters));
                 ctx->launches++;
             }
             return RTGPU_OK;
@@ -1132,7 +1157,7 @@ int render_wavefront(rtgpu_context* ctx, const T* d_reals, const rt::CameraParam
         if (st < 0) return st;
         if (st == 0) {
             if (counters) {
-                wf_commit_counters_kernel<<<1, 32, 0, stream>>>(ctx->d_wf_priv, counters);
+                CUDA_TRY(launch_chain(wf_commit_counters_kernel, 1u, 32u, 0, stream, true, (const unsigned long long*)ctx->d_wf_priv, counters));
                 ctx->launches++;
             }
             CUDA_TRY(cudaGetLastError());
@@ -1298,7 +1323,8 @@ void* mapped_device_pointer(const void* host) {
 // The frame's kernels are all enqueued: publish what the host will want to read once the stream has drained.
 int publish_status(rtgpu_context* ctx) {
     ctx->h_status->valid = 0u;
-    publish_status_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_counters, ctx->wf_used ? ctx->d_wf_counts : nullptr, ctx->d_status);
+    CUDA_TRY(launch_chain(publish_status_kernel, 1u, 32u, 0, ctx->stream, true, (const unsigned long long*)ctx->d_counters,
+                          (const rt::WfCounts*)(ctx->wf_used ? ctx->d_wf_counts : nullptr), ctx->d_status));
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
     return RTGPU_OK;
