@@ -309,7 +309,7 @@ CALIBRATION_FRAMES = 4  # 2 per kernel family (TUNE_RUNS in csrc/rtgpu.cu)
 
 
 PROFILED_TRAFFIC = {  # (scene, width, height, precision, depth, family) -> committed ncu per-launch list of one frame
-    ("cover", 1920, 1080, "f64", 6, "wavefront"): "profiles/r2c_wavefront_launches.csv",
+    ("cover", 1920, 1080, "f64", 6, "wavefront"): "profiles/r2d_wavefront_launches.csv",
     ("synthetic:100000", 7680, 4320, "f64", 6, "wavefront"): "profiles/r2_synthetic_1e5_8k_launches.csv",
 }
 
@@ -531,7 +531,7 @@ def run_b200(args):
         roofline = {
             "bound": "fp64_fma_pipe" if args.precision == "f64" else "fp32_fma_pipe", "achieved": achieved, "peak": peak_tflops,
             "unit": "TFLOP/s", "frac": achieved / peak_tflops, "traffic": traffic, "traffic_source": traffic_source,
-            "kernel": "rt::wf_level_kernel x (max_depth + 1) = 87 % of the step (profiles/r2c_wavefront_launches.md); achieved = "
+            "kernel": "rt::wf_level_kernel x (max_depth + 1) = 87 % of the step (profiles/r2d_wavefront_launches.md); achieved = "
                       "frame flops / frame time" if family_used == "wavefront" else "rt::render_kernel (the whole step)",
             "peak_source": "measured live: 8 independent FMA chains per thread on every SM (rtgpu_measure_fma_peak); "
                            "MEASURED_PEAKS.json holds only HBM and bf16 peaks",
@@ -539,7 +539,7 @@ def run_b200(args):
             "frac_note": "frac = the reference's brute-force flops (every shape tested exactly for every ray, SURVEY 8d) / time / peak: the "
                          "kernels skip most of those tests with a single-precision bounding-sphere pre-test, so frac is a speed relative to a "
                          "brute-force machine at peak, not pipe occupancy (profiled FP64 pipe: 26-31 % busy, issue slots 63-73 %, "
-                         "profiles/r2c_wavefront_launches.md)",
+                         "profiles/r2d_wavefront_launches.md)",
             "traffic_model": traffic_model, "traffic_model_source": "in-run: device record counts (rtgpu_context_frame_records) x record sizes + the frame write",
             "hbm": {"achieved_gbs": (traffic or traffic_model) / (device_ms / K * 1e-3) / 1e9 / world, "peak_gbs": hbm_peak, "peak_source": hbm_peak_source,
                     "frac": (traffic or traffic_model) / (device_ms / K * 1e-3) / 1e9 / world / hbm_peak,

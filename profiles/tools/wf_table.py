@@ -62,7 +62,7 @@ level-0 launch): with the node state parked in shared memory the level kernels r
 instruction counts and threads per instruction are those of round 1 — the divergence of the exact tests at depth
 (17.6-25 threads per instruction at levels 1-6) is unchanged and is what is left.  The combine kernels (9.6 % of the
 frame) are memory-latency bound at ~3.8 TB/s.""",
-    "r2c_wavefront_launches.csv": """
+    "r2d_wavefront_launches.csv": """
 Reading (end of round 2: single-precision pre-test, binned queues): a level's queue is consumed grouped by (hit shape,
 reflected / refracted), which lifts the deeper levels from 17.9-25.3 to **21.9-29.3 threads per instruction**; the
 pre-test no longer touches the FP64 pipe (26-31 % busy instead of 47-52 %: what is left there are the exact tests), issue
