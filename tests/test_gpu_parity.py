@@ -591,3 +591,22 @@ def test_binned_queues_render_the_same_bits(monkeypatch, scene, width, height, p
         got, got8, stats = r.render(cam, family="wavefront", precision=precision)
     assert np.array_equal(got.view(bits), want.view(bits)) and np.array_equal(got8, want8)
     assert {k: stats[k] for k in COUNTERS} == {k: wstats[k] for k in COUNTERS}
+
+
+@pytest.mark.gpu
+def test_launch_count_tells_binned_from_plain_frames(monkeypatch):
+    """rtgpu_context_launch_count counts at the launch sites: a host-buffer frame of the wavefront family is a level and
+    a combine kernel per recursion level plus the status block (15 at depth 6), a binned one six more; the persistent
+    family one kernel plus the status block.  Below 2^18 pixels the default gate leaves the queues in arrival order."""
+    flat, camera = load_scene_fixture("cover")
+    cam = camera.resized(320, 180)
+    with Renderer(flat) as r:
+        n0 = r.launch_count()
+        r.render(cam, family="wavefront", want_rgb8=False)
+        n1 = r.launch_count()
+        r.render(cam, family="persistent", want_rgb8=False)
+        n2 = r.launch_count()
+        monkeypatch.setenv("RTGPU_WF_BINS", "1")
+        r.render(cam, family="wavefront", want_rgb8=False)
+        n3 = r.launch_count()
+    assert (n1 - n0, n2 - n1, n3 - n2) == (2 * 7 + 1, 1 + 1, 2 * 7 + 6 + 1)
