@@ -1403,8 +1403,8 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
     // Wavefront family, whole frame: render it in two interleaved parts (16-row bands) and copy the first part while
     // the second one renders; the queues are reused.  The parts are UNEQUAL: with T(f) ~ 0.25 + 1.62 f ms for a
     // fraction f of the 1080p cover frame and 0.94 f ms for its copy, the first part should be as large as the
-    // second part's kernels can still hide its copy (f ~ 0.7): 3 of every 4 bands, then the fourth — 2.60 -> 2.42 ms
-    // end to end against equal halves.  RTGPU_E2E_SPLIT=<take>/<period> overrides, RTGPU_E2E_CHUNKS=1 disables.
+    // second part's kernels can still hide its copy (f ~ 0.7): 7 of every 10 bands, then the other three — 2.60 -> 2.42 ms
+    // end to end against equal halves at the time.  RTGPU_E2E_SPLIT=<take>/<period> overrides, RTGPU_E2E_CHUNKS=1 disables.
     const char* chunks_env = getenv("RTGPU_E2E_CHUNKS");
     // Only for pinned host buffers: a device-to-host copy into pageable memory blocks the submitting thread, so the
     // second part's kernels would not even be enqueued before the first part's copy has finished.
@@ -1418,7 +1418,10 @@ int enqueue_host_render(rtgpu_context* ctx, const rtgpu_camera* camera, const rt
             CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
         }
         constexpr uint32_t BAND = 16, CHUNKS = 2;
-        uint32_t take0 = 3, period = 4;  // 1/2 2.60, 3/5 2.50, 2/3 2.46, 7/10 2.42, 3/4 2.42, 4/5 2.45 ms (cover@1080p)
+        // cover@1080p end to end, ms — kernels 1.875: 1/2 2.60, 3/5 2.50, 2/3 2.46, 7/10 2.42, 3/4 2.42, 4/5 2.45; kernels 1.67
+        // (end of round 2): 2/3 2.19, 7/10 2.17, 5/7 2.20, 3/4 2.24: the faster the kernels, the smaller the first part
+        // whose copy the second part's kernels can still hide
+        uint32_t take0 = 7, period = 10;
         if (const char* sp = getenv("RTGPU_E2E_SPLIT"); sp && *sp) {
             unsigned a = 0, b = 0;
             if (sscanf(sp, "%u/%u", &a, &b) == 2 && a >= 1 && b >= 2 && a < b && b <= 64) {
