@@ -866,11 +866,12 @@ void tune_end(rtgpu_context* ctx, cudaStream_t stream, uint64_t key, int family)
     ctx->tune_pending_key = key;
 }
 
-// First guess of the wavefront buffers per pixel of a launch.  The cover frame peaks at 0.63 queued hits and 1.5 node
-// records per pixel; glass-heavy frames ask for more and get it through the overflow -> enlarge -> render-again path,
+// First guess of the wavefront buffers per pixel of a launch.  The cover frame peaks at 0.63 queued hits per pixel in one
+// level and needs 2.09 node records per pixel over all levels (2.0 made the first frame of every context overflow at
+// level 5 and render twice); glass-heavy frames ask for more and get it through the overflow -> enlarge -> render-again path,
 // once (the buffers are kept).  Small on purpose: the first frame of a process pays for allocating and first touching
 // them (3 + 5 per pixel = 1.7 GB at 1080p cost a cold call ~1 s and its first frame 15 ms instead of 2).
-constexpr double WF_RAYS_PER_PIXEL = 1.0, WF_NODES_PER_PIXEL = 2.0;
+constexpr double WF_RAYS_PER_PIXEL = 1.0, WF_NODES_PER_PIXEL = 2.25;
 // Binned queues pay where the deeper launches are large and bound by divergence over a longer shape list: at least half
 // of the shapes reflective or transparent (cover 18 of 19: -4.4 %; reflect_refract 7 of 13: -2.5 %; table 6 of 18: +-0;
 // cylinders 3 of 11: +5 %), at least 8 shapes (scenes of 3-6 shapes: +6..8 % when forced on) and 2^18 pixels per launch
