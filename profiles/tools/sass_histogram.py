@@ -44,12 +44,16 @@ def main():
     print("Blackwell data movement: **UBLKCP {} (cp.async.bulk), SYNCS {} (mbarrier)**; tensor-core opcodes (HMMA / UTCMMA / "
           "tcgen05): {} — by design, the path is scalar FP64.\n".format(total["UBLKCP"], total["SYNCS"],
                                                                          sum(v for k, v in total.items() if "MMA" in k)))
-    print("| scope | instr | DFMA | DMUL | DADD | DSETP | MUFU | LDS | STS | LDL | STL | LDG | STG | BRA | BSSY+BSYNC | UBLKCP | SYNCS |")
-    print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
+    print("Programmatic dependent launch: **PREEXIT {} (griddepcontrol.launch_dependents), ACQBULK {} (griddepcontrol.wait)**.  "
+          "Single precision beside the FP64 exact tests (bounding-sphere pre-test, BVH box tests): FFMA {}, FSETP {}; packed FFMA2 {}.\n".format(
+              total["PREEXIT"], total["ACQBULK"], total["FFMA"], total["FSETP"], total["FFMA2"]))
+    print("| scope | instr | DFMA | DMUL | DADD | DSETP | MUFU | FFMA | FSETP | LDS | STS | LDL | STL | LDG | STG | BRA | BSSY+BSYNC | UBLKCP | SYNCS | PREEXIT | ACQBULK |")
+    print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
 
     def row(name, c):
-        cols = ["DFMA", "DMUL", "DADD", "DSETP", "MUFU", "LDS", "STS", "LDL", "STL", "LDG", "STG", "BRA"]
-        print(f"| {name} | {sum(c.values())} | " + " | ".join(str(c[k]) for k in cols) + f" | {c['BSSY'] + c['BSYNC']} | {c['UBLKCP']} | {c['SYNCS']} |")
+        cols = ["DFMA", "DMUL", "DADD", "DSETP", "MUFU", "FFMA", "FSETP", "LDS", "STS", "LDL", "STL", "LDG", "STG", "BRA"]
+        print(f"| {name} | {sum(c.values())} | " + " | ".join(str(c[k]) for k in cols) +
+              f" | {c['BSSY'] + c['BSYNC']} | {c['UBLKCP']} | {c['SYNCS']} | {c['PREEXIT']} | {c['ACQBULK']} |")
 
     row("whole library", total)
     for label, key in HOT.items():
