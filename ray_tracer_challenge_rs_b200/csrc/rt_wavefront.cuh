@@ -650,8 +650,10 @@ __global__ void __launch_bounds__(256) wf_bin_kernel(const WfCounts* __restrict_
 
 template <typename T>
 __global__ void wf_combine_kernel(WfNode<T>* __restrict__ nodes, const WfCounts* __restrict__ counts, int level, unsigned cap_nodes,
-                                  T* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8) {
-    wf_release_dependents();
+                                  T* __restrict__ out_rgb, uint8_t* __restrict__ out_rgb8, int release) {
+    // release: another kernel of THIS library follows (it waits before it reads).  The last kernel of a frame never
+    // releases early: whatever the caller launches next on the stream must see a finished frame.
+    if (release) wf_release_dependents();
     wf_wait_for_previous();
     const unsigned begin = level == 0 ? 0u : min(counts->node_end[level - 1], cap_nodes);
     const unsigned end = min(counts->node_end[level], cap_nodes);

@@ -731,8 +731,7 @@ int launch_kernel_impl(rtgpu_context* ctx, const T* d_reals, const rt::CameraPar
 #endif
 
 __global__ void wf_commit_counters_kernel(const unsigned long long* priv, unsigned long long* user) {
-    rt::wf_release_dependents();
-    rt::wf_wait_for_previous();
+    rt::wf_wait_for_previous();  // (no early release: this may be the last kernel of the frame)
     if (threadIdx.x < rt::NUM_COUNTERS && priv[threadIdx.x]) atomicAdd(&user[threadIdx.x], priv[threadIdx.x]);
 }
 
@@ -981,7 +980,6 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
                     (void*)ctx->d_wf_priv, ctx->d_wf_nodes, ctx->d_wf_rays[0], ctx->d_wf_rays[1], ctx->wf_cap_rays, ctx->wf_cap_nodes);
     CUDA_TRY(cudaMemsetAsync(ctx->d_wf_counts, 0, ctx->wf_keep_overflow ? offsetof(rt::WfCounts, overflow) : sizeof(rt::WfCounts), stream));
     CUDA_TRY(cudaMemsetAsync(ctx->d_wf_priv, 0, rt::NUM_COUNTERS * sizeof(unsigned long long), stream));
-    (void)d_counters;
     rt::WfNode<T>* nodes = reinterpret_cast<rt::WfNode<T>*>(ctx->d_wf_nodes);
     // Binned queues for scenes whose whole shape list fits the bins (rt_wavefront.cuh RT_WF_BINS); small launches are
     // bound by launch latency, not by divergence, and skip the extra kernel per level.  RTGPU_WF_BINS=0 / 1 forces it.
@@ -1024,7 +1022,8 @@ int launch_wavefront_impl(rtgpu_context* ctx, const T* d_reals, const rt::Camera
     }
     for (int level = levels - 1; level >= 0; --level)
         CUDA_TRY(launch_chain(rt::wf_combine_kernel<T>, (unsigned)ctx->sm_count * RT_WF_COMBINE_CTAS, 256u, 0, stream, !debug_sync, nodes,
-                              (const rt::WfCounts*)ctx->d_wf_counts, level, (unsigned)ctx->wf_cap_nodes, d_out, d_out8));
+                              (const rt::WfCounts*)ctx->d_wf_counts, level, (unsigned)ctx->wf_cap_nodes, d_out, d_out8,
+                              (level > 0 || d_counters != nullptr) ? 1 : 0));  // the counter commit follows the last pass
     ctx->launches += (uint64_t)levels;
     CUDA_TRY(cudaGetLastError());
     ctx->wf_used = true;
