@@ -274,6 +274,25 @@ def time_oracle_serial_sample(flat, camera, max_depth: int, stride: int = 16):
     return st["rays"] / dt / 1e6, int(px.size)
 
 
+def time_oracle_native(args):
+    """the same CPU restatement built with -march=native ON THIS HOST (oracle/Makefile `native`),
+    timed through this script's own reference arm in a child process; the favourable-to-CPU number beside the bit-parity
+    build.  Returns a dict for cpu_baseline["native"]."""
+    try:
+        from oracle import oracle as O
+
+        lib = O.build_native()
+        env = dict(os.environ, RTORACLE_LIBRARY=lib)
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1", "--scene", args.scene, "--width", str(args.width),
+               "--height", str(args.height), "--max-depth", str(args.max_depth)]
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        return {"value": line["value"], "unit": line["unit"], "cores": line["cpu_baseline"]["cores"], "ms_per_frame": line["ms_per_step"],
+                "flags": "-O3 -march=native -ffp-contract=off (same bits as the parity build)"}
+    except Exception as exc:  # no compiler on the box, ...: the parity build's number stands alone
+        return {"unavailable": str(exc)[:200]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -559,7 +578,8 @@ def run_b200(args):
                 cpu = {"value": ostats["rays"] / min(times) / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
                        "sample": f"the same whole {args.width}x{args.height} frame, best of 3; restated reference (C + OpenMP), not rustc output",
                        "ms_per_frame": min(times) * 1e3,
-                       "serial": {"value": serial_mrays, "unit": "Mrays/s", "cores": 1, "sample": f"every 16th pixel of the frame ({serial_px} pixels), one thread"}}
+                       "serial": {"value": serial_mrays, "unit": "Mrays/s", "cores": 1, "sample": f"every 16th pixel of the frame ({serial_px} pixels), one thread"},
+                       "native": time_oracle_native(args)}
                 device_rgb = frame_device
             else:
                 times, ostats, cores, oracle_rgb = time_oracle(flat, camera, args.max_depth, steps=1, warmup=0, pixels=sample)

@@ -18,7 +18,9 @@ from ray_tracer_challenge_rs_b200 import abi
 from ray_tracer_challenge_rs_b200.flatten import FlatScene, camera_to_c
 
 ORACLE_DIR = os.path.dirname(os.path.abspath(__file__))
-LIBRARY_PATH = os.path.join(ORACLE_DIR, "librtoracle.so")
+# RTORACLE_LIBRARY: another build of the same source (bench.py times the -march=native variant through it)
+LIBRARY_PATH = os.environ.get("RTORACLE_LIBRARY") or os.path.join(ORACLE_DIR, "librtoracle.so")
+NATIVE_LIBRARY_PATH = os.path.join(ORACLE_DIR, "_native", "librtoracle_native.so")
 
 _pd = C.POINTER(C.c_double)
 
@@ -58,6 +60,15 @@ def build(force: bool = False) -> str:
         raise RuntimeError("make not found")
     subprocess.run([make, "-C", ORACLE_DIR, "-B" if force else "-s"], check=True, env=env, capture_output=True)
     return LIBRARY_PATH
+
+
+def build_native() -> str:
+    """Compile the -march=native variant for THIS host (always rebuilt: the flags depend on the CPU it runs on)."""
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CFLAGS", None)
+    subprocess.run([shutil.which("make") or "make", "-C", ORACLE_DIR, "-B", "native"], check=True, env=env, capture_output=True)
+    return NATIVE_LIBRARY_PATH
 
 
 _lib: Optional[C.CDLL] = None
