@@ -5,13 +5,17 @@
 // intersection the query cares about still runs, in the reference's arithmetic, so results are
 // unchanged (boxes are inflated far beyond f64 rounding, and hit selection is by (distance, world
 // order), independent of visiting order).  Binned-SAH top-down build, one shape per leaf, children
-// boxes stored in the parent (2 box tests per node visit).
+// boxes stored in the parent (2 box tests per node visit); large scenes are built by several threads, with a result
+// that does not depend on how many.
 #pragma once
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <future>
 #include <limits>
+#include <thread>
 #include <vector>
 
 namespace rt {
@@ -56,7 +60,150 @@ struct Bvh {
 };
 
 // items: boxes of the bounded shapes.  Leaves reference positions in `leaf_order`.
-inline Bvh build_bvh(const std::vector<Aabb>& boxes, int depth_limit) {
+//
+// The tree is binary with one item per leaf, emitted in depth-first order, left subtree first: the subtree over the
+// items [begin, end) of the (partitioned) index array owns exactly the nodes [r, r + count - 1) and the leaves
+// [begin, end), where r is its root's index, its left child sits at r + 1 and its right child at r + (mid - begin).
+// Every index is therefore known before anything below it is built, the arrays can be sized up front, and disjoint
+// subtrees can be built by different threads into their own slices: the result does not depend on the thread count
+// (tests/test_bvh_build.py).  threads = 0: as many as the host offers.
+namespace bvh_detail {
+
+struct Build {
+    const std::vector<Aabb>& boxes;
+    std::vector<uint32_t>& idx;
+    const double* cen[3];
+    Bvh& out;
+    int depth_limit;
+    std::atomic<int> max_depth{0};
+    Build(const std::vector<Aabb>& b, std::vector<uint32_t>& i, Bvh& o, int limit) : boxes(b), idx(i), out(o), depth_limit(limit) {}
+};
+
+struct Task {
+    uint32_t begin, end;
+    uint32_t node;  // index of the subtree's root node (unused for a single item)
+    int depth;
+};
+
+// Splits [begin, end) (count >= 2) and writes the node; returns the split position.
+inline uint32_t split_range(Build& B, const Task& t) {
+    std::vector<uint32_t>& idx = B.idx;
+    const std::vector<Aabb>& boxes = B.boxes;
+    const uint32_t count = t.end - t.begin;
+    constexpr int BINS = 16;
+    // centroid bounds -> split axis
+    double clo[3] = {1e300, 1e300, 1e300}, chi[3] = {-1e300, -1e300, -1e300};
+    for (uint32_t i = t.begin; i < t.end; ++i)
+        for (int k = 0; k < 3; ++k) {
+            clo[k] = std::min(clo[k], B.cen[k][idx[i]]);
+            chi[k] = std::max(chi[k], B.cen[k][idx[i]]);
+        }
+    int axis = 0;
+    if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
+    if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
+    uint32_t mid = t.begin + count / 2;
+    const double extent = chi[axis] - clo[axis];
+    bool split_done = false;
+    if (extent > 0 && count > 4 && t.depth + (int)std::ceil(std::log2((double)count)) + 2 < B.depth_limit) {
+        // binned SAH
+        Aabb bb[BINS];
+        uint32_t bc[BINS] = {0};
+        for (auto& b : bb) b.reset();
+        const double scale = BINS * (1.0 - 1e-9) / extent;
+        for (uint32_t i = t.begin; i < t.end; ++i) {
+            int b = (int)((B.cen[axis][idx[i]] - clo[axis]) * scale);
+            b = std::min(std::max(b, 0), BINS - 1);
+            bb[b].grow(boxes[idx[i]]);
+            bc[b]++;
+        }
+        double right_area[BINS];
+        uint32_t right_count[BINS];
+        Aabb acc;
+        acc.reset();
+        uint32_t cnt = 0;
+        for (int b = BINS - 1; b >= 1; --b) {
+            acc.grow(bb[b]);
+            cnt += bc[b];
+            right_area[b] = acc.half_area();
+            right_count[b] = cnt;
+        }
+        acc.reset();
+        cnt = 0;
+        double best = std::numeric_limits<double>::infinity();
+        int best_split = -1;
+        for (int b = 0; b < BINS - 1; ++b) {
+            acc.grow(bb[b]);
+            cnt += bc[b];
+            if (cnt == 0 || right_count[b + 1] == 0) continue;
+            const double cost = acc.half_area() * cnt + right_area[b + 1] * right_count[b + 1];
+            if (cost < best) {
+                best = cost;
+                best_split = b;
+            }
+        }
+        if (best_split >= 0) {
+            const double thr_bin = best_split + 1;
+            auto it = std::partition(idx.begin() + t.begin, idx.begin() + t.end, [&](uint32_t v) {
+                int b = (int)((B.cen[axis][v] - clo[axis]) * scale);
+                b = std::min(std::max(b, 0), BINS - 1);
+                return b < thr_bin;
+            });
+            mid = (uint32_t)(it - idx.begin());
+            split_done = mid > t.begin && mid < t.end;
+        }
+    }
+    if (!split_done) {
+        mid = t.begin + count / 2;
+        std::nth_element(idx.begin() + t.begin, idx.begin() + mid, idx.begin() + t.end,
+                         [&](uint32_t a, uint32_t b) { return B.cen[axis][a] < B.cen[axis][b]; });
+    }
+    BvhNode& node = B.out.nodes[t.node];
+    node.box[0].reset();
+    node.box[1].reset();
+    for (uint32_t i = t.begin; i < mid; ++i) node.box[0].grow(boxes[idx[i]]);
+    for (uint32_t i = mid; i < t.end; ++i) node.box[1].grow(boxes[idx[i]]);
+    // children by the layout rule above: a single item is the leaf at its own position in the index array
+    node.child[0] = mid - t.begin == 1 ? ~(int32_t)t.begin : (int32_t)(t.node + 1u);
+    node.child[1] = t.end - mid == 1 ? ~(int32_t)mid : (int32_t)(t.node + (mid - t.begin));
+    return mid;
+}
+
+// Builds the subtree of one task on the calling thread; subtrees of at least `spawn_min` items found on the way down are
+// handed to other threads while fewer than `spawn_depth` splits lie above them.
+inline void build_subtree(Build& B, Task root, uint32_t spawn_min, int spawn_depth) {
+    std::vector<Task> stack;
+    std::vector<std::future<void>> spawned;
+    stack.push_back(root);
+    int deepest = 0;
+    while (!stack.empty()) {
+        const Task t = stack.back();
+        stack.pop_back();
+        deepest = std::max(deepest, t.depth);
+        if (t.end - t.begin == 1) {
+            B.out.leaf_order[t.begin] = B.idx[t.begin];
+            continue;
+        }
+        const uint32_t mid = split_range(B, t);
+        const Task left{t.begin, mid, t.node + 1u, t.depth + 1}, right{mid, t.end, t.node + (mid - t.begin), t.depth + 1};
+        if (t.depth - root.depth < spawn_depth && mid - t.begin >= spawn_min && t.end - mid >= spawn_min) {
+            spawned.push_back(std::async(std::launch::async, [&B, left, spawn_min, spawn_depth, &root, t] {
+                build_subtree(B, left, spawn_min, spawn_depth - (t.depth + 1 - root.depth));
+            }));
+            stack.push_back(right);
+        } else {
+            stack.push_back(right);
+            stack.push_back(left);
+        }
+    }
+    int seen = B.max_depth.load();
+    while (deepest > seen && !B.max_depth.compare_exchange_weak(seen, deepest)) {
+    }
+    for (auto& f : spawned) f.get();
+}
+
+}  // namespace bvh_detail
+
+inline Bvh build_bvh(const std::vector<Aabb>& boxes, int depth_limit, unsigned threads = 0) {
     Bvh bvh;
     const uint32_t n = (uint32_t)boxes.size();
     if (n == 0) return bvh;
@@ -68,115 +215,24 @@ inline Bvh build_bvh(const std::vector<Aabb>& boxes, int depth_limit) {
         cy[i] = 0.5 * (boxes[i].lo[1] + boxes[i].hi[1]);
         cz[i] = 0.5 * (boxes[i].lo[2] + boxes[i].hi[2]);
     }
-    const double* cen[3] = {cx.data(), cy.data(), cz.data()};
-    bvh.leaf_order.reserve(n);
+    bvh.leaf_order.assign(n, 0u);
     if (n == 1) {
-        bvh.leaf_order.push_back(0);
         bvh.root = ~0;
         return bvh;
     }
-    bvh.nodes.reserve(n - 1);
-
-    struct Task {
-        uint32_t begin, end;
-        int32_t parent;  // node whose child slot receives the result, -1 for the root
-        int slot;
-        int depth;
-    };
-    // depth-first with an explicit stack; right child pushed first so the left subtree is emitted first
-    std::vector<Task> stack;
-    stack.push_back({0, n, -1, 0, 1});
-    constexpr int BINS = 16;
-    while (!stack.empty()) {
-        Task t = stack.back();
-        stack.pop_back();
-        const uint32_t count = t.end - t.begin;
-        bvh.max_depth = std::max(bvh.max_depth, t.depth);
-        int32_t ref;
-        if (count == 1) {
-            ref = ~(int32_t)bvh.leaf_order.size();
-            bvh.leaf_order.push_back(idx[t.begin]);
-        } else {
-            // centroid bounds -> split axis
-            double clo[3] = {1e300, 1e300, 1e300}, chi[3] = {-1e300, -1e300, -1e300};
-            for (uint32_t i = t.begin; i < t.end; ++i)
-                for (int k = 0; k < 3; ++k) {
-                    clo[k] = std::min(clo[k], cen[k][idx[i]]);
-                    chi[k] = std::max(chi[k], cen[k][idx[i]]);
-                }
-            int axis = 0;
-            if (chi[1] - clo[1] > chi[axis] - clo[axis]) axis = 1;
-            if (chi[2] - clo[2] > chi[axis] - clo[axis]) axis = 2;
-            uint32_t mid = t.begin + count / 2;
-            const double extent = chi[axis] - clo[axis];
-            bool split_done = false;
-            if (extent > 0 && count > 4 && t.depth + (int)std::ceil(std::log2((double)count)) + 2 < depth_limit) {
-                // binned SAH
-                Aabb bb[BINS];
-                uint32_t bc[BINS] = {0};
-                for (auto& b : bb) b.reset();
-                const double scale = BINS * (1.0 - 1e-9) / extent;
-                for (uint32_t i = t.begin; i < t.end; ++i) {
-                    int b = (int)((cen[axis][idx[i]] - clo[axis]) * scale);
-                    b = std::min(std::max(b, 0), BINS - 1);
-                    bb[b].grow(boxes[idx[i]]);
-                    bc[b]++;
-                }
-                double right_area[BINS];
-                uint32_t right_count[BINS];
-                Aabb acc;
-                acc.reset();
-                uint32_t cnt = 0;
-                for (int b = BINS - 1; b >= 1; --b) {
-                    acc.grow(bb[b]);
-                    cnt += bc[b];
-                    right_area[b] = acc.half_area();
-                    right_count[b] = cnt;
-                }
-                acc.reset();
-                cnt = 0;
-                double best = std::numeric_limits<double>::infinity();
-                int best_split = -1;
-                for (int b = 0; b < BINS - 1; ++b) {
-                    acc.grow(bb[b]);
-                    cnt += bc[b];
-                    if (cnt == 0 || right_count[b + 1] == 0) continue;
-                    const double cost = acc.half_area() * cnt + right_area[b + 1] * right_count[b + 1];
-                    if (cost < best) {
-                        best = cost;
-                        best_split = b;
-                    }
-                }
-                if (best_split >= 0) {
-                    const double thr_bin = best_split + 1;
-                    auto it = std::partition(idx.begin() + t.begin, idx.begin() + t.end, [&](uint32_t v) {
-                        int b = (int)((cen[axis][v] - clo[axis]) * scale);
-                        b = std::min(std::max(b, 0), BINS - 1);
-                        return b < thr_bin;
-                    });
-                    mid = (uint32_t)(it - idx.begin());
-                    split_done = mid > t.begin && mid < t.end;
-                }
-            }
-            if (!split_done) {
-                mid = t.begin + count / 2;
-                std::nth_element(idx.begin() + t.begin, idx.begin() + mid, idx.begin() + t.end,
-                                 [&](uint32_t a, uint32_t b) { return cen[axis][a] < cen[axis][b]; });
-            }
-            ref = (int32_t)bvh.nodes.size();
-            BvhNode node;
-            node.box[0].reset();
-            node.box[1].reset();
-            for (uint32_t i = t.begin; i < mid; ++i) node.box[0].grow(boxes[idx[i]]);
-            for (uint32_t i = mid; i < t.end; ++i) node.box[1].grow(boxes[idx[i]]);
-            node.child[0] = node.child[1] = 0;
-            bvh.nodes.push_back(node);
-            stack.push_back({mid, t.end, ref, 1, t.depth + 1});
-            stack.push_back({t.begin, mid, ref, 0, t.depth + 1});
-        }
-        if (t.parent < 0) bvh.root = ref;
-        else bvh.nodes[t.parent].child[t.slot] = ref;
-    }
+    bvh.nodes.resize(n - 1);
+    bvh.root = 0;
+    bvh_detail::Build B(boxes, idx, bvh, depth_limit);
+    B.cen[0] = cx.data();
+    B.cen[1] = cy.data();
+    B.cen[2] = cz.data();
+    if (threads == 0) threads = std::max(1u, std::thread::hardware_concurrency());
+    // up to 2^spawn_depth subtrees in flight; small scenes are built on the calling thread
+    int spawn_depth = 0;
+    while ((1u << spawn_depth) < 2u * threads && spawn_depth < 8) ++spawn_depth;
+    if (threads <= 1 || n < (1u << 15)) spawn_depth = 0;
+    bvh_detail::build_subtree(B, bvh_detail::Task{0u, n, 0u, 1}, std::max(1u << 12, n >> (spawn_depth + 2)), spawn_depth);
+    bvh.max_depth = B.max_depth.load();
     return bvh;
 }
 

@@ -286,9 +286,39 @@ uint32_t bvh_threshold() {
     return 32;
 }
 
+double wall_ms();
+
+// fn(begin, end, worker) over [0, n) in contiguous chunks on several threads (the calling one included) when there is
+// enough to share out; the packer's per-shape and per-node loops are independent iterations writing disjoint records.
+template <typename F>
+void parallel_for(uint32_t n, uint32_t min_chunk, F&& fn) {
+    unsigned workers = std::max(1u, std::thread::hardware_concurrency());
+    workers = std::min<unsigned>(workers, std::max<uint32_t>(1u, n / std::max(1u, min_chunk)));
+    workers = std::min(workers, 64u);
+    if (workers <= 1) {
+        fn(0u, n, 0u);
+        return;
+    }
+    const uint32_t chunk = (n + workers - 1) / workers;
+    std::vector<std::thread> pool;
+    for (unsigned w = 1; w < workers; ++w) pool.emplace_back([&fn, w, chunk, n] { fn(std::min(n, w * chunk), std::min(n, (w + 1) * chunk), w); });
+    fn(0u, std::min(n, chunk), 0u);
+    for (auto& t : pool) t.join();
+}
+
 int pack_scene(const rtgpu_scene* s, PackedScene* out) {
+    // RTGPU_PACK_TRACE=1: where the host time of packing a (large) scene goes, on stderr
+    const bool pack_trace = getenv("RTGPU_PACK_TRACE") != nullptr;
+    double t_mark = pack_trace ? wall_ms() : 0.0;
+    auto mark = [&](const char* what) {
+        if (!pack_trace) return;
+        const double now = wall_ms();
+        fprintf(stderr, "[rtgpu] pack: %-34s %8.2f ms\n", what, now - t_mark);
+        t_mark = now;
+    };
     int st = validate_scene(s);
     if (st != RTGPU_OK) return st;
+    mark("validate");
     const uint32_t S = s->n_shapes, M = s->n_materials, Q = s->n_patterns, L = s->n_lights;
     rt::SceneLayout& lay = out->layout;
     memset(&lay, 0, sizeof(lay));
@@ -303,10 +333,11 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     std::vector<rt::Aabb> boxes(S);
     std::vector<uint8_t> bounded(S, 0);
     uint32_t n_bounded = 0;
-    for (uint32_t i = 0; i < S; ++i) {
-        bounded[i] = bounding_box(s, i, &boxes[i]) ? 1 : 0;
-        n_bounded += bounded[i];
-    }
+    parallel_for(S, 1u << 14, [&](uint32_t begin, uint32_t end, unsigned) {
+        for (uint32_t i = begin; i < end; ++i) bounded[i] = bounding_box(s, i, &boxes[i]) ? 1 : 0;
+    });
+    for (uint32_t i = 0; i < S; ++i) n_bounded += bounded[i];
+    mark("bounding boxes");
     const uint32_t threshold = bvh_threshold();
     // (a hierarchy over a single shape would be one half-empty node whose empty box no slab test rejects: keep it flat)
     const bool use_bvh = threshold > 0 && n_bounded >= std::max(threshold, 2u);
@@ -332,7 +363,9 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
                 items.push_back(i);
                 item_boxes.push_back(boxes[i]);
             }
+        mark("order + item boxes");
         bvh = rt::build_bvh(item_boxes, rt::BVH_MAX_DEPTH);
+        mark("BVH build");
         if (bvh.max_depth >= rt::BVH_MAX_DEPTH) return fail(RTGPU_ERR_UNSUPPORTED, "BVH depth %d exceeds the device stack", bvh.max_depth);
         for (uint32_t k = 0; k < bvh.leaf_order.size(); ++k) order.push_back(items[bvh.leaf_order[k]]);
     }
@@ -383,8 +416,21 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     double* R = out->reals.data();
     int* I = out->ints.data();
 
-    uint32_t tri_slot = 0;
-    for (uint32_t pos = 0; pos < S; ++pos) {
+    mark("layout + blob allocation");
+    // triangles get their slots in sorted order: a prefix count, so that the loop below has independent iterations
+    std::vector<uint32_t> tri_slot_at;
+    if (n_tri) {
+        tri_slot_at.resize(S);
+        uint32_t running = 0;
+        for (uint32_t pos = 0; pos < S; ++pos) {
+            tri_slot_at[pos] = running;
+            running += s->shape_type[order[pos]] == RTGPU_TRIANGLE ? 1u : 0u;
+        }
+    }
+    float cull_coord_max_of[64] = {0};
+    parallel_for(S, 1u << 13, [&](uint32_t pos_begin, uint32_t pos_end, unsigned worker) {
+    float coord_max_local = 0.0f;
+    for (uint32_t pos = pos_begin; pos < pos_end; ++pos) {
         const uint32_t i = order[pos];
         double* g = R + (size_t)pos * rt::SHAPE_REALS;
         memcpy(g, s->shape_inv + (size_t)i * 12, 12 * sizeof(double));
@@ -418,22 +464,26 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
             if (std::isfinite(c64[3]))
                 for (int k = 0; k < 3; ++k) {
                     const float a = std::nextafterf(std::fabs(c32[k]), std::numeric_limits<float>::infinity());
-                    if (!std::isfinite(a)) lay.cull_coord_max = std::numeric_limits<float>::infinity();  // the kernel then never culls
-                    else if (a > lay.cull_coord_max) lay.cull_coord_max = a;
+                    if (!std::isfinite(a)) coord_max_local = std::numeric_limits<float>::infinity();  // the kernel then never culls
+                    else if (a > coord_max_local) coord_max_local = a;
                 }
             memcpy(I + lay.cull32_off + (size_t)pos * 4, c32, sizeof(c32));
         }
         if (s->shape_type[i] == RTGPU_TRIANGLE) {
             const size_t t = (size_t)s->shape_triangle[i] * 3;
+            const uint32_t tri_slot = tri_slot_at[pos];
             m[4] = (int)tri_slot;
             double* td = R + lay.tri_off + (size_t)tri_slot * rt::TRI_REALS;
-            ++tri_slot;
             memcpy(td + 0, s->tri_vertex_1 + t, 3 * sizeof(double));
             memcpy(td + 3, s->tri_edge_1 + t, 3 * sizeof(double));
             memcpy(td + 6, s->tri_edge_2 + t, 3 * sizeof(double));
             memcpy(td + 9, s->tri_normal + t, 3 * sizeof(double));
         }
     }
+    cull_coord_max_of[worker] = coord_max_local;
+    });
+    for (float v : cull_coord_max_of) lay.cull_coord_max = std::max(lay.cull_coord_max, v);  // (inf stays inf)
+    mark("shapes (records, cull spheres)");
     for (uint32_t m = 0; m < M; ++m) {
         double* d = R + lay.mat_off + (size_t)m * rt::MAT_REALS;
         memcpy(d, s->mat_color + (size_t)m * 3, 3 * sizeof(double));
@@ -483,12 +533,15 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
             I[lay.bvh_meta_off + k * rt::BVH_INTS + 1] = leaf_ref(bvh.nodes[k].child[1]);
         }
     }
+    mark("materials, patterns, lights, nodes");
     if (use_bvh) {
         // single-precision node copies: boxes rounded outwards, children alongside (rt_scene.h BVH32_WORDS)
         auto down = [](double v) { float f = (float)v; return ((double)f > v) ? std::nextafterf(f, -std::numeric_limits<float>::infinity()) : f; };
         auto up = [](double v) { float f = (float)v; return ((double)f < v) ? std::nextafterf(f, std::numeric_limits<float>::infinity()) : f; };
+        float coord_max_of[64] = {0};
+        parallel_for(lay.n_bvh_nodes, 1u << 14, [&](uint32_t k_begin, uint32_t k_end, unsigned worker) {
         float coord_max = 0.0f;
-        for (uint32_t k = 0; k < lay.n_bvh_nodes; ++k) {
+        for (uint32_t k = k_begin; k < k_end; ++k) {
             const double* nb = R + lay.bvh_off + (size_t)k * rt::BVH_REALS;
             int* w = I + lay.bvh32_off + (size_t)k * rt::BVH32_WORDS;
             float f[12];
@@ -504,8 +557,13 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
             w[13] = I[lay.bvh_meta_off + k * rt::BVH_INTS + 1];
             w[14] = w[15] = 0;
         }
+        coord_max_of[worker] = coord_max;
+        });
+        float coord_max = 0.0f;
+        for (float v : coord_max_of) coord_max = std::max(coord_max, v);
         lay.bvh_coord_max = coord_max;
     }
+    mark("single-precision nodes");
     // FNV-1a over (a sample of) the blobs: tells the family tuner whether two uploads are the same scene
     uint64_t fp = 1469598103934665603ull;
     auto mix = [&fp](uint64_t v) { fp = (fp ^ v) * 1099511628211ull; };
@@ -519,6 +577,7 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     }
     for (size_t k = 0; k < out->ints.size(); k += step_i) mix((uint64_t)(uint32_t)out->ints[k]);
     out->fingerprint = fp;
+    mark("fingerprint");
     return RTGPU_OK;
 }
 
