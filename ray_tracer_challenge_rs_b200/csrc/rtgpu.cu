@@ -54,9 +54,26 @@ int fail(int status, const char* fmt, ...) {
 // ---------------------------------------------------------------------------------------------
 // Scene packer: rtgpu_scene (world order, SoA) -> the two device blobs of rt_scene.h (type-sorted).
 
+// resize() without value-initialisation: the packer zeroes (first-touches) the blobs of a large scene on several threads
+template <typename T>
+struct NoInitAllocator : std::allocator<T> {
+    template <typename U>
+    struct rebind {
+        using other = NoInitAllocator<U>;
+    };
+    template <typename U>
+    void construct(U* p) noexcept {
+        ::new (static_cast<void*>(p)) U;
+    }
+    template <typename U, typename... Args>
+    void construct(U* p, Args&&... args) {
+        ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...);
+    }
+};
+
 struct PackedScene {
-    std::vector<double> reals;
-    std::vector<int> ints;
+    std::vector<double, NoInitAllocator<double>> reals;
+    std::vector<int, NoInitAllocator<int>> ints;
     rt::SceneLayout layout;
     bool has_cyl_cone_tri = false;
     bool has_secondary = false;  // some material is reflective or transparent: rays beyond primary + shadow exist
@@ -411,10 +428,14 @@ int pack_scene(const rtgpu_scene* s, PackedScene* out) {
     if ((uint64_t)S * rt::SHAPE_REALS + (uint64_t)n_tri * rt::TRI_REALS + (uint64_t)S * rt::CULL_REALS + (uint64_t)lay.n_bvh_nodes * rt::BVH_REALS > 0xF0000000ull)
         return fail(RTGPU_ERR_UNSUPPORTED, "scene too large for 32-bit blob offsets (%u shapes)", S);
 
-    out->reals.assign(lay.n_reals, 0.0);
-    out->ints.assign(lay.n_ints, 0);
+    out->reals.clear();
+    out->ints.clear();
+    out->reals.resize(lay.n_reals);  // no initialisation (NoInitAllocator): zeroed below, in parallel
+    out->ints.resize(lay.n_ints);
     double* R = out->reals.data();
     int* I = out->ints.data();
+    parallel_for(lay.n_reals, 1u << 18, [&](uint32_t b, uint32_t e, unsigned) { memset(R + b, 0, (size_t)(e - b) * sizeof(double)); });
+    parallel_for(lay.n_ints, 1u << 19, [&](uint32_t b, uint32_t e, unsigned) { memset(I + b, 0, (size_t)(e - b) * sizeof(int)); });
 
     mark("layout + blob allocation");
     // triangles get their slots in sorted order: a prefix count, so that the loop below has independent iterations
